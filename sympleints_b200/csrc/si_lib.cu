@@ -1,0 +1,1082 @@
+// sympleints_b200 -- CUDA kernels and C ABI (see include/sympleints_b200.h).
+//
+// Kernels: one warp per shell tuple ("slot").  A slot owns a work array W and a
+// scalar table S in shared memory and executes the stage program of its class
+// (si_machine.h): per primitive tuple the Boys values and geometry scalars are
+// staged into shared memory, the vertical recurrences run stage by stage with
+// __syncwarp() in between, the primitive contraction accumulates into X, then
+// cart->sph on c, the horizontal recurrence and the remaining cart->sph
+// transforms run once per contracted tuple.  Work is handed out through a
+// global atomic counter (cost-sorted item lists) so that unevenly contracted
+// shells do not leave SMs idle.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/sympleints_b200.h"
+#include "si_machine.h"
+#include "si_program.h"
+
+// ---------------------------------------------------------------------------
+// device-side data
+// ---------------------------------------------------------------------------
+struct BasisDev {
+    const int* L;
+    const int* nprim;
+    const int* poff;
+    const int* foff;  // function offsets (sph or cart, chosen by the host)
+    const double* cen;
+    const double* exps;
+    const double* coef;
+};
+
+struct SiPairItem {
+    int sa, sb;       // shell indices; L(sa) >= L(sb)
+    int swapped;      // packed layout: 1 if sa is the column shell of the (i>=j) block
+    int pad;
+    long long prow;   // first row of the pair block in the packed 3-index layout
+};
+
+enum StoreMode { STORE_BLOCK = 0, STORE_MATRIX = 1, STORE_3C_FULL = 2, STORE_3C_PACKED = 3 };
+
+struct OutDesc {
+    double* out;
+    long long ld;           // matrix: nbf ; 3c: naux_local
+    long long comp_stride;  // matrix: nbf*nbf
+    long long nbf;
+    int mode;
+};
+
+__device__ __forceinline__ long long next_item(int* counter, int lane) {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(counter, 1);
+    return (long long)__shfl_sync(0xffffffffu, v, 0);
+}
+
+__device__ __forceinline__ void load_consts(const SiProg& P, double* S, int lane) {
+    for (int c = lane; c < P.nconst; c += 32) S[SI_NDYN + c] = P.consts[c];
+}
+
+__device__ __forceinline__ void contracted_phase(const SiProg& P, double* W, double* S, const double* A,
+                                                 const double* B, int lane) {
+    auto sync = [] { __syncwarp(); };
+    __syncwarp();
+    {
+        double v[12], kb[5];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) v[q] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) kb[q] = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) v[6 + d] = A[d] - B[d];
+        si_fill_scalars(S, v, kb, 0.0, lane, 32);
+    }
+    si_run_stages(P, P.n_prim_stages, P.chunk_begin, W, S, 0, 1, lane, 32, sync);
+    for (int m0 = 0; m0 < P.nb_total; m0 += P.chunk) {
+        const int nb = min(P.chunk, P.nb_total - m0);
+        si_run_stages(P, P.chunk_begin, P.nstages, W, S, m0, nb, lane, 32, sync);
+    }
+    __syncwarp();
+}
+
+// Store the final block W[out_off ...] of a 2-index key.
+__device__ __forceinline__ void store_matrix(const SiProg& P, const double* W, const OutDesc& od, int fa,
+                                             int fb, bool diag, int lane) {
+    const int n0 = P.out_n0, n1 = P.out_n1, nb = P.nb_total;
+    const int n01 = n0 * n1;
+    const int total = n01 * nb;
+    for (int idx = lane; idx < total; idx += 32) {
+        const double val = W[P.out_off + idx];
+        if (od.mode == STORE_BLOCK) {
+            od.out[idx] = val;
+            continue;
+        }
+        int b, i, j;
+        if (P.out_batch_major) {
+            b = idx / n01;
+            int r = idx - b * n01;
+            i = r / n1;
+            j = r - i * n1;
+        } else {
+            b = idx % nb;
+            int r = idx / nb;
+            i = r / n1;
+            j = r - i * n1;
+        }
+        double* o = od.out + (long long)b * od.comp_stride;
+        o[(long long)(fa + i) * od.ld + (fb + j)] = val;
+        if (!diag) o[(long long)(fb + j) * od.ld + (fa + i)] = val;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+// 1e (ovlp, kin, dpm, qpm, dqpm) and 2c2e: one warp per shell pair.
+__global__ void __launch_bounds__(256) k_two_index(SiProg P, SiBoys Bt, BasisDev bs, const SiPairItem* items,
+                                                   int nitems, int is_2c2e, double Rx, double Ry, double Rz,
+                                                   OutDesc od, int* counter) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (P.w_size + SI_NDYN + P.nconst + 1) & ~1;
+    double* W = smem + (size_t)warp * per;
+    double* S = W + P.w_size;
+    load_consts(P, S, lane);
+    auto sync = [] { __syncwarp(); };
+    const double R[3] = {Rx, Ry, Rz};
+    for (long long item = next_item(counter, lane); item < nitems; item = next_item(counter, lane)) {
+        const SiPairItem it = items[item];
+        const int Ka = bs.nprim[it.sa], Kb = bs.nprim[it.sb];
+        const int pa = bs.poff[it.sa], pb = bs.poff[it.sb];
+        double A[3], B[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            A[d] = bs.cen[3 * it.sa + d];
+            B[d] = bs.cen[3 * it.sb + d];
+        }
+        __syncwarp();
+        for (int i = lane; i < P.x_size; i += 32) W[P.x_off + i] = 0.0;
+        for (int i = 0; i < Ka; ++i) {
+            const double ax = bs.exps[pa + i], da = bs.coef[pa + i];
+            for (int j = 0; j < Kb; ++j) {
+                const double bx = bs.exps[pb + j], db = bs.coef[pb + j];
+                __syncwarp();
+                if (is_2c2e)
+                    si_setup_2c2e(P, Bt, ax, da, A, bx, db, B, W, S, lane, 32);
+                else
+                    si_setup_1e(P, ax, da, A, bx, db, B, R, W, S, lane, 32);
+                si_run_stages(P, 0, P.n_prim_stages, W, S, 0, 1, lane, 32, sync);
+            }
+        }
+        contracted_phase(P, W, S, A, B, lane);
+        store_matrix(P, W, od, bs.foff ? bs.foff[it.sa] : 0, bs.foff ? bs.foff[it.sb] : 0, it.sa == it.sb, lane);
+    }
+}
+
+// coul: one CTA per shell pair; the warps split the point charges, their partial
+// [a0] accumulators are summed in shared memory, warp 0 finishes the pair.
+__global__ void __launch_bounds__(256) k_coul(SiProg P, SiBoys Bt, BasisDev bs, const SiPairItem* items,
+                                              int nitems, const double* cxyz, const double* cq, int ncharge,
+                                              OutDesc od) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int per = (P.w_size + SI_NDYN + P.nconst + 1) & ~1;
+    double* W = smem + (size_t)warp * per;
+    double* S = W + P.w_size;
+    load_consts(P, S, lane);
+    auto sync = [] { __syncwarp(); };
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const SiPairItem it = items[item];
+        const int Ka = bs.nprim[it.sa], Kb = bs.nprim[it.sb];
+        const int pa = bs.poff[it.sa], pb = bs.poff[it.sb];
+        double A[3], B[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            A[d] = bs.cen[3 * it.sa + d];
+            B[d] = bs.cen[3 * it.sb + d];
+        }
+        __syncthreads();
+        for (int i = lane; i < P.x_size; i += 32) W[P.x_off + i] = 0.0;
+        for (int i = 0; i < Ka; ++i) {
+            const double ax = bs.exps[pa + i], da = bs.coef[pa + i];
+            for (int j = 0; j < Kb; ++j) {
+                const double bx = bs.exps[pb + j], db = bs.coef[pb + j];
+                for (int c = warp; c < ncharge; c += nw) {
+                    const double Rc[3] = {cxyz[3 * c], cxyz[3 * c + 1], cxyz[3 * c + 2]};
+                    __syncwarp();
+                    si_setup_coul(P, Bt, ax, da, A, bx, db, B, Rc, cq[c], W, S, lane, 32);
+                    si_run_stages(P, 0, P.n_prim_stages, W, S, 0, 1, lane, 32, sync);
+                }
+            }
+        }
+        __syncthreads();
+        // reduce the per-warp accumulators into warp 0's X (fixed order: deterministic)
+        for (int i = threadIdx.x; i < P.x_size; i += blockDim.x) {
+            double s = smem[P.x_off + i];
+            for (int w = 1; w < nw; ++w) s += smem[(size_t)w * per + P.x_off + i];
+            smem[P.x_off + i] = s;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            contracted_phase(P, W, S, A, B, lane);
+            store_matrix(P, W, od, bs.foff ? bs.foff[it.sa] : 0, bs.foff ? bs.foff[it.sb] : 0, it.sa == it.sb,
+                         lane);
+        }
+    }
+}
+
+// 3c2e: one warp per (shell pair, auxiliary shell).
+__global__ void __launch_bounds__(256) k_3c2e(SiProg P, SiBoys Bt, BasisDev orb, BasisDev aux,
+                                              const SiPairItem* pairs, int npairs, const int* auxlist,
+                                              int naux_c, int col_begin, OutDesc od, int* counter) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (P.w_size + SI_NDYN + P.nconst + 1) & ~1;
+    double* W = smem + (size_t)warp * per;
+    double* S = W + P.w_size;
+    load_consts(P, S, lane);
+    auto sync = [] { __syncwarp(); };
+    const long long nitems = (long long)npairs * naux_c;
+    for (long long item = next_item(counter, lane); item < nitems; item = next_item(counter, lane)) {
+        const int ip = (int)(item / naux_c);
+        const int ic = (int)(item - (long long)ip * naux_c);
+        const SiPairItem it = pairs[ip];
+        const int sc = auxlist ? auxlist[ic] : ic;
+        const int Ka = orb.nprim[it.sa], Kb = orb.nprim[it.sb], Kc = aux.nprim[sc];
+        const int pa = orb.poff[it.sa], pb = orb.poff[it.sb], pc = aux.poff[sc];
+        double A[3], B[3], C[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            A[d] = orb.cen[3 * it.sa + d];
+            B[d] = orb.cen[3 * it.sb + d];
+            C[d] = aux.cen[3 * sc + d];
+        }
+        __syncwarp();
+        for (int i = lane; i < P.x_size; i += 32) W[P.x_off + i] = 0.0;
+        for (int i = 0; i < Ka; ++i) {
+            const double ax = orb.exps[pa + i], da = orb.coef[pa + i];
+            for (int j = 0; j < Kb; ++j) {
+                const double bx = orb.exps[pb + j], db = orb.coef[pb + j];
+                for (int k = 0; k < Kc; ++k) {
+                    const double cx = aux.exps[pc + k], dc = aux.coef[pc + k];
+                    __syncwarp();
+                    si_setup_3c2e(P, Bt, ax, da, A, bx, db, B, cx, dc, C, W, S, lane, 32);
+                    si_run_stages(P, 0, P.n_prim_stages, W, S, 0, 1, lane, 32, sync);
+                }
+            }
+        }
+        contracted_phase(P, W, S, A, B, lane);
+        // store: W[out_off + (i*n1 + j)*nm + m]
+        const int n0 = P.out_n0, n1 = P.out_n1, nm = P.nb_total;
+        const int total = n0 * n1 * nm;
+        if (od.mode == STORE_BLOCK) {
+            for (int idx = lane; idx < total; idx += 32) od.out[idx] = W[P.out_off + idx];
+        } else {
+            const long long col = (long long)(aux.foff[sc] - col_begin);
+            const int fa = orb.foff[it.sa], fb = orb.foff[it.sb];
+            for (int idx = lane; idx < total; idx += 32) {
+                const int m = idx % nm;
+                const int r = idx / nm;
+                const int i = r / n1;
+                const int j = r - i * n1;
+                const double val = W[P.out_off + idx];
+                if (od.mode == STORE_3C_FULL) {
+                    od.out[((long long)(fa + i) * od.nbf + (fb + j)) * od.ld + col + m] = val;
+                    if (it.sa != it.sb) od.out[((long long)(fb + j) * od.nbf + (fa + i)) * od.ld + col + m] = val;
+                } else {
+                    const long long row = it.swapped ? it.prow + (long long)j * n0 + i : it.prow + (long long)i * n1 + j;
+                    od.out[row * od.ld + col + m] = val;
+                }
+            }
+        }
+    }
+}
+
+__global__ void k_boys_eval(SiBoys Bt, int n, const double* x, size_t nx, double* out) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < nx) out[i] = si_boys(Bt, n, x[i]);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+#define SI_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            g_last_error = std::string(#call) + ": " + cudaGetErrorString(_e);                 \
+            return SI_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+struct DevProgram {
+    SiProgramHost host;
+    SiProg dev;
+    void* d_hdr = nullptr;
+    void* d_terms = nullptr;
+    void* d_stages = nullptr;
+    void* d_consts = nullptr;
+};
+
+static const int SI_NSTREAMS = 8;
+static const int SI_NCOUNTERS = 1024;
+
+struct si_context {
+    int device = 0;
+    int lmax = 0, lauxmax = 0;
+    int sm_count = 148;
+    int max_smem = 227 * 1024;
+    std::vector<double> boys_host;
+    std::vector<double> pref_host;
+    int nrows = 0, ncols = 0;
+    double* d_boys = nullptr;
+    double* d_pref = nullptr;
+    SiBoys boys_dev;
+    std::map<std::tuple<int, int, int, int, int, int>, DevProgram*> progs;
+    long long launches = 0;
+    cudaStream_t streams[SI_NSTREAMS];
+    cudaEvent_t ev_fork;
+    cudaEvent_t ev_join[SI_NSTREAMS];
+    int* d_counters = nullptr;
+    int next_counter = 0;
+};
+
+struct si_basis {
+    si_context* ctx = nullptr;
+    int nshell = 0;
+    std::vector<int> L, nprim, poff, foff_sph, foff_cart;
+    std::vector<double> cen, exps, coef, coef_pgto;
+    int nbf_sph = 0, nbf_cart = 0, lmax = 0;
+    long long packed_rows = 0;
+    int *d_L = nullptr, *d_nprim = nullptr, *d_poff = nullptr, *d_foff_sph = nullptr, *d_foff_cart = nullptr;
+    double *d_cen = nullptr, *d_exps = nullptr, *d_coef = nullptr, *d_coef_pgto = nullptr;
+    // shell-pair classes (La >= Lb), cost-sorted, on the device
+    struct PairClass {
+        int La, Lb;
+        int n = 0;
+        SiPairItem* d_items = nullptr;
+    };
+    std::vector<PairClass> pair_classes;
+    // aux shells by angular momentum
+    struct AuxClass {
+        int Lc;
+        std::vector<int> shells;
+    };
+    bool pairs_built = false;
+};
+
+const char* si_strerror(int status) {
+    switch (status) {
+        case SI_OK: return "ok";
+        case SI_ERR_ARG: return "invalid argument";
+        case SI_ERR_LMAX: return "angular momentum exceeds lmax/lauxmax of the context";
+        case SI_ERR_CUDA: return "CUDA error";
+        case SI_ERR_KEY: return "unknown integral key or unsupported option";
+        case SI_ERR_BOYS: return "Boys order exceeds the table";
+        default: return "internal error";
+    }
+}
+const char* si_last_error(void) { return g_last_error.c_str(); }
+
+// Boys table with the reference algorithm (testing/boys.py:18-29,81-91); the top row is
+// evaluated with the convergent series F_n(x) = exp(-x) sum_k (2x)^k / ((2n+1)(2n+3)...(2n+2k+1))
+// in extended precision instead of adaptive quadrature.
+static void build_boys_table(int nmax, std::vector<double>& table, int& nrows, int& ncols) {
+    const int order = 6;
+    nrows = nmax + order + 1;
+    ncols = 301;
+    table.assign((size_t)nrows * ncols, 0.0);
+    std::vector<double> xs(ncols);
+    for (int i = 0; i < ncols; ++i) {
+        // numpy.linspace(0, 30, 301): start + i*step with step = 30/300
+        const double step = 30.0 / 300.0;
+        xs[i] = (i == ncols - 1) ? 30.0 : 0.0 + i * step;
+    }
+    const int ntop = nmax + order;
+    for (int i = 0; i < ncols; ++i) {
+        long double x = xs[i];
+        long double term = 1.0L / (2 * ntop + 1);
+        long double sum = term;
+        for (int k = 1; k < 2000; ++k) {
+            term *= 2.0L * x / (2 * ntop + 2 * k + 1);
+            sum += term;
+            if (term < 1e-22L * sum) break;
+        }
+        table[(size_t)ntop * ncols + i] = (double)(expl(-x) * sum);
+    }
+    for (int n = ntop - 1; n >= 0; --n)
+        for (int i = 0; i < ncols; ++i) {
+            double emx = std::exp(-xs[i]);
+            table[(size_t)n * ncols + i] = (2.0 * xs[i] * table[(size_t)(n + 1) * ncols + i] + emx) / (2 * n + 1);
+        }
+}
+
+int si_init(int device, int lmax, int lauxmax, const double* boys_table, int nrows, int ncols, si_context** out) {
+    if (!out || lmax < 0 || lauxmax < 0) return SI_ERR_ARG;
+    if (lmax > 5 || lauxmax > 2 * 5) {
+        g_last_error = "lmax <= 5 and lauxmax <= 10 supported";
+        return SI_ERR_LMAX;
+    }
+    int ndev = 0;
+    SI_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) {
+        g_last_error = "no such CUDA device";
+        return SI_ERR_CUDA;
+    }
+    SI_CUDA(cudaSetDevice(device));
+    si_context* c = new si_context;
+    c->device = device;
+    c->lmax = lmax;
+    c->lauxmax = lauxmax;
+    cudaDeviceProp prop;
+    SI_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem = (int)prop.sharedMemPerBlockOptin;
+    if (boys_table) {
+        if (ncols != 301 || nrows < 8) {
+            delete c;
+            return SI_ERR_ARG;
+        }
+        c->boys_host.assign(boys_table, boys_table + (size_t)nrows * ncols);
+        c->nrows = nrows;
+        c->ncols = ncols;
+    } else {
+        int need = std::max(2 * lmax + lauxmax, 2 * lauxmax);  // highest Boys order
+        build_boys_table(std::max(need, 8), c->boys_host, c->nrows, c->ncols);
+    }
+    const int nmax = c->nrows - 7;
+    c->pref_host.resize(nmax + 1);
+    for (int n = 0; n <= nmax; ++n) {
+        double f2 = 1.0;
+        for (int k = 2 * n - 1; k > 1; k -= 2) f2 *= k;
+        c->pref_host[n] = f2 / std::pow(2.0, n + 1) * std::sqrt(SI_PI);
+    }
+    SI_CUDA(cudaMalloc(&c->d_boys, c->boys_host.size() * sizeof(double)));
+    SI_CUDA(cudaMemcpy(c->d_boys, c->boys_host.data(), c->boys_host.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SI_CUDA(cudaMalloc(&c->d_pref, c->pref_host.size() * sizeof(double)));
+    SI_CUDA(cudaMemcpy(c->d_pref, c->pref_host.data(), c->pref_host.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->boys_dev.table = c->d_boys;
+    c->boys_dev.xlarge_pref = c->d_pref;
+    c->boys_dev.nrows = c->nrows;
+    c->boys_dev.ncols = c->ncols;
+    for (int i = 0; i < SI_NSTREAMS; ++i) {
+        SI_CUDA(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
+        SI_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+    SI_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    SI_CUDA(cudaMalloc(&c->d_counters, SI_NCOUNTERS * sizeof(int)));
+    SI_CUDA(cudaFuncSetAttribute(k_two_index, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    SI_CUDA(cudaFuncSetAttribute(k_coul, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    SI_CUDA(cudaFuncSetAttribute(k_3c2e, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    *out = c;
+    return SI_OK;
+}
+
+static void free_program(DevProgram* p) {
+    cudaFree(p->d_hdr);
+    cudaFree(p->d_terms);
+    cudaFree(p->d_stages);
+    cudaFree(p->d_consts);
+    delete p;
+}
+
+int si_finalize(si_context* c) {
+    if (!c) return SI_ERR_ARG;
+    cudaSetDevice(c->device);
+    for (auto& kv : c->progs) free_program(kv.second);
+    for (int i = 0; i < SI_NSTREAMS; ++i) {
+        cudaStreamDestroy(c->streams[i]);
+        cudaEventDestroy(c->ev_join[i]);
+    }
+    cudaEventDestroy(c->ev_fork);
+    cudaFree(c->d_boys);
+    cudaFree(c->d_pref);
+    cudaFree(c->d_counters);
+    delete c;
+    return SI_OK;
+}
+
+int si_boys_table(const si_context* c, double* table, int* nrows, int* ncols) {
+    if (!c) return SI_ERR_ARG;
+    if (nrows) *nrows = c->nrows;
+    if (ncols) *ncols = c->ncols;
+    if (table) memcpy(table, c->boys_host.data(), c->boys_host.size() * sizeof(double));
+    return SI_OK;
+}
+
+int si_boys_eval(si_context* c, int n, const double* x, size_t nx, double* out) {
+    if (!c || !x || !out) return SI_ERR_ARG;
+    if (n < 0 || n > c->nrows - 7) return SI_ERR_BOYS;
+    SI_CUDA(cudaSetDevice(c->device));
+    double *dx = nullptr, *dout = nullptr;
+    SI_CUDA(cudaMalloc(&dx, nx * sizeof(double)));
+    SI_CUDA(cudaMalloc(&dout, nx * sizeof(double)));
+    SI_CUDA(cudaMemcpy(dx, x, nx * sizeof(double), cudaMemcpyHostToDevice));
+    k_boys_eval<<<(unsigned)((nx + 255) / 256), 256>>>(c->boys_dev, n, dx, nx, dout);
+    c->launches++;
+    SI_CUDA(cudaGetLastError());
+    SI_CUDA(cudaMemcpy(out, dout, nx * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dx);
+    cudaFree(dout);
+    return SI_OK;
+}
+
+static int get_program(si_context* c, int key, int La, int Lb, int Lc, int sph, int normalize, DevProgram** out) {
+    auto k = std::make_tuple(key, La, Lb, Lc, sph, normalize ? 1 : 0);
+    auto it = c->progs.find(k);
+    if (it != c->progs.end()) {
+        *out = it->second;
+        return SI_OK;
+    }
+    DevProgram* p = new DevProgram;
+    try {
+        p->host = si_build_program(key, La, Lb, Lc, sph, normalize ? 1 : 0);
+    } catch (std::exception& e) {
+        g_last_error = e.what();
+        delete p;
+        return SI_ERR_INTERNAL;
+    }
+    const SiProgramHost& h = p->host;
+    // Boys orders needed vs table
+    if (key == SI_KEY_COUL || key == SI_KEY_2C2E || key == SI_KEY_3C2E) {
+        if (h.desc.boys_nlo + h.desc.nbase - 1 > c->nrows - 7) {
+            g_last_error = "Boys table too small for this class";
+            delete p;
+            return SI_ERR_BOYS;
+        }
+    }
+    auto up = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 8));
+        if (e != cudaSuccess) return e;
+        if (bytes) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+        return e;
+    };
+    SI_CUDA(up(h.hdr.data(), h.hdr.size() * 4, &p->d_hdr));
+    SI_CUDA(up(h.terms.data(), h.terms.size() * 4, &p->d_terms));
+    SI_CUDA(up(h.stages.data(), h.stages.size() * sizeof(SiStage), &p->d_stages));
+    SI_CUDA(up(h.consts.data(), h.consts.size() * 8, &p->d_consts));
+    p->dev = h.desc;
+    p->dev.hdr = (const uint32_t*)p->d_hdr;
+    p->dev.terms = (const uint32_t*)p->d_terms;
+    p->dev.stages = (const SiStage*)p->d_stages;
+    p->dev.consts = (const double*)p->d_consts;
+    c->progs[k] = p;
+    *out = p;
+    return SI_OK;
+}
+
+int si_class_stats(si_context* c, int key, int La, int Lb, int Lc, int sph, int normalize, long long* out) {
+    if (!c || !out) return SI_ERR_ARG;
+    if (La < Lb) std::swap(La, Lb);
+    DevProgram* p;
+    int rc = get_program(c, key, La, Lb, Lc, sph, normalize, &p);
+    if (rc) return rc;
+    out[0] = p->host.n_fma_prim;
+    out[1] = p->host.n_fma_contr;
+    out[2] = p->host.desc.w_size + SI_NDYN + p->host.desc.nconst;
+    out[3] = (long long)(p->host.hdr.size() + p->host.terms.size());
+    return SI_OK;
+}
+
+long long si_launch_count(const si_context* c) { return c ? c->launches : -1; }
+
+// ---------------------------------------------------------------------------
+// basis
+// ---------------------------------------------------------------------------
+template <typename T>
+static cudaError_t upload(const std::vector<T>& v, T** d) {
+    cudaError_t e = cudaMalloc((void**)d, std::max<size_t>(v.size() * sizeof(T), 8));
+    if (e != cudaSuccess) return e;
+    if (!v.empty()) e = cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+int si_basis_create(si_context* c, int nshell, const int* L, const int* nprim, const double* centers,
+                    const double* exps, const double* coefs, si_basis** out) {
+    if (!c || !out || nshell <= 0 || !L || !nprim || !centers || !exps || !coefs) return SI_ERR_ARG;
+    SI_CUDA(cudaSetDevice(c->device));
+    si_basis* b = new si_basis;
+    b->ctx = c;
+    b->nshell = nshell;
+    b->L.assign(L, L + nshell);
+    b->nprim.assign(nprim, nprim + nshell);
+    b->cen.assign(centers, centers + 3 * (size_t)nshell);
+    int np = 0, fs = 0, fc = 0;
+    long long prow = 0;
+    for (int i = 0; i < nshell; ++i) {
+        if (L[i] < 0 || L[i] > std::max(c->lmax, c->lauxmax) || nprim[i] <= 0) {
+            delete b;
+            g_last_error = "shell angular momentum exceeds lmax/lauxmax (or nprim <= 0)";
+            return SI_ERR_LMAX;
+        }
+        b->poff.push_back(np);
+        np += nprim[i];
+        b->foff_sph.push_back(fs);
+        b->foff_cart.push_back(fc);
+        fs += si_nsph(L[i]);
+        fc += si_ncart(L[i]);
+        b->lmax = std::max(b->lmax, L[i]);
+    }
+    b->nbf_sph = fs;
+    b->nbf_cart = fc;
+    for (int i = 0; i < nshell; ++i)
+        for (int j = 0; j <= i; ++j) prow += (long long)si_nsph(L[i]) * si_nsph(L[j]);
+    b->packed_rows = prow;
+    b->exps.assign(exps, exps + np);
+    b->coef.assign(coefs, coefs + np);
+    // --normalize pgto: radial part of norm_pgto (main.py:152-159) folded into the coefficients
+    b->coef_pgto.resize(np);
+    for (int i = 0; i < nshell; ++i)
+        for (int k = 0; k < nprim[i]; ++k) {
+            int idx = b->poff[i] + k;
+            double a = b->exps[idx];
+            int l = L[i];
+            b->coef_pgto[idx] = b->coef[idx] * std::sqrt(std::pow(2.0, 2 * l + 1.5) * std::pow(a, l + 1.5) /
+                                                         std::pow(SI_PI, 1.5));
+        }
+    SI_CUDA(upload(b->L, &b->d_L));
+    SI_CUDA(upload(b->nprim, &b->d_nprim));
+    SI_CUDA(upload(b->poff, &b->d_poff));
+    SI_CUDA(upload(b->foff_sph, &b->d_foff_sph));
+    SI_CUDA(upload(b->foff_cart, &b->d_foff_cart));
+    SI_CUDA(upload(b->cen, &b->d_cen));
+    SI_CUDA(upload(b->exps, &b->d_exps));
+    SI_CUDA(upload(b->coef, &b->d_coef));
+    SI_CUDA(upload(b->coef_pgto, &b->d_coef_pgto));
+    *out = b;
+    return SI_OK;
+}
+
+int si_basis_destroy(si_basis* b) {
+    if (!b) return SI_ERR_ARG;
+    cudaSetDevice(b->ctx->device);
+    cudaFree(b->d_L);
+    cudaFree(b->d_nprim);
+    cudaFree(b->d_poff);
+    cudaFree(b->d_foff_sph);
+    cudaFree(b->d_foff_cart);
+    cudaFree(b->d_cen);
+    cudaFree(b->d_exps);
+    cudaFree(b->d_coef);
+    cudaFree(b->d_coef_pgto);
+    for (auto& pc : b->pair_classes) cudaFree(pc.d_items);
+    delete b;
+    return SI_OK;
+}
+
+int si_basis_nbf(const si_basis* b, int sph) { return b ? (sph ? b->nbf_sph : b->nbf_cart) : -1; }
+int si_basis_nshell(const si_basis* b) { return b ? b->nshell : -1; }
+long long si_basis_packed_rows(const si_basis* b) { return b ? b->packed_rows : -1; }
+
+// Host shell-batcher: sort the shell pairs i >= j into (La >= Lb) classes, most
+// expensive (most primitive pairs) first.
+static int build_pair_classes(si_basis* b) {
+    if (b->pairs_built) return SI_OK;
+    std::map<std::pair<int, int>, std::vector<SiPairItem>> cls;
+    long long prow = 0;
+    for (int i = 0; i < b->nshell; ++i)
+        for (int j = 0; j <= i; ++j) {
+            SiPairItem it;
+            memset(&it, 0, sizeof(it));
+            if (b->L[i] >= b->L[j]) {
+                it.sa = i;
+                it.sb = j;
+                it.swapped = 0;
+            } else {
+                it.sa = j;
+                it.sb = i;
+                it.swapped = 1;
+            }
+            it.prow = prow;
+            prow += (long long)si_nsph(b->L[i]) * si_nsph(b->L[j]);
+            cls[{b->L[it.sa], b->L[it.sb]}].push_back(it);
+        }
+    for (auto& kv : cls) {
+        auto& v = kv.second;
+        std::stable_sort(v.begin(), v.end(), [&](const SiPairItem& x, const SiPairItem& y) {
+            return b->nprim[x.sa] * b->nprim[x.sb] > b->nprim[y.sa] * b->nprim[y.sb];
+        });
+        si_basis::PairClass pc;
+        pc.La = kv.first.first;
+        pc.Lb = kv.first.second;
+        pc.n = (int)v.size();
+        SI_CUDA(cudaMalloc((void**)&pc.d_items, v.size() * sizeof(SiPairItem)));
+        SI_CUDA(cudaMemcpy(pc.d_items, v.data(), v.size() * sizeof(SiPairItem), cudaMemcpyHostToDevice));
+        b->pair_classes.push_back(pc);
+    }
+    b->pairs_built = true;
+    return SI_OK;
+}
+
+static BasisDev basis_dev(const si_basis* b, int sph, int normalize) {
+    BasisDev d;
+    d.L = b->d_L;
+    d.nprim = b->d_nprim;
+    d.poff = b->d_poff;
+    d.foff = sph ? b->d_foff_sph : b->d_foff_cart;
+    d.cen = b->d_cen;
+    d.exps = b->d_exps;
+    d.coef = (normalize == SI_NORM_PGTO) ? b->d_coef_pgto : b->d_coef;
+    return d;
+}
+
+// fork/join helpers: class launches fan out over the context's streams
+struct Fan {
+    si_context* c;
+    cudaStream_t user;
+    int next = 0;
+    bool used[SI_NSTREAMS];
+    int begin() {
+        memset(used, 0, sizeof(used));
+        SI_CUDA(cudaMemsetAsync(c->d_counters, 0, SI_NCOUNTERS * sizeof(int), user));
+        c->next_counter = 0;
+        SI_CUDA(cudaEventRecord(c->ev_fork, user));
+        return SI_OK;
+    }
+    int stream(cudaStream_t* s) {
+        int i = next++ % SI_NSTREAMS;
+        if (!used[i]) {
+            SI_CUDA(cudaStreamWaitEvent(c->streams[i], c->ev_fork, 0));
+            used[i] = true;
+        }
+        *s = c->streams[i];
+        return SI_OK;
+    }
+    int end() {
+        for (int i = 0; i < SI_NSTREAMS; ++i)
+            if (used[i]) {
+                SI_CUDA(cudaEventRecord(c->ev_join[i], c->streams[i]));
+                SI_CUDA(cudaStreamWaitEvent(user, c->ev_join[i], 0));
+            }
+        return SI_OK;
+    }
+};
+
+static int pick_warps(const si_context* c, const SiProg& P, int max_warps, size_t* smem_bytes) {
+    const size_t per = (size_t)((P.w_size + SI_NDYN + P.nconst + 1) & ~1) * sizeof(double);
+    int nw = (int)std::min<size_t>((size_t)max_warps, (size_t)c->max_smem / per);
+    if (nw < 1) return 0;
+    *smem_bytes = per * nw;
+    return nw;
+}
+
+static int check_key_2idx(int key) {
+    return (key == SI_OVLP || key == SI_KIN || key == SI_DPM || key == SI_QPM || key == SI_DQPM) ? 1 : 0;
+}
+
+static int run_two_index(si_context* c, const si_basis* cb, int key, int sph, int normalize, const double* R,
+                         int ncharge, const double* d_cxyz, const double* d_q, double* out_dev, cudaStream_t user) {
+    si_basis* b = const_cast<si_basis*>(cb);
+    SI_CUDA(cudaSetDevice(c->device));
+    int rc = build_pair_classes(b);
+    if (rc) return rc;
+    const int lim = (key == SI_2C2E) ? c->lauxmax : c->lmax;
+    if (b->lmax > lim) {
+        g_last_error = "basis angular momentum exceeds the context limit for this key";
+        return SI_ERR_LMAX;
+    }
+    const long long nbf = sph ? b->nbf_sph : b->nbf_cart;
+    OutDesc od;
+    od.out = out_dev;
+    od.ld = nbf;
+    od.comp_stride = nbf * nbf;
+    od.nbf = nbf;
+    od.mode = STORE_MATRIX;
+    BasisDev bd = basis_dev(b, sph, normalize);
+    Fan fan{c, user};
+    rc = fan.begin();
+    if (rc) return rc;
+    for (auto& pc : b->pair_classes) {
+        DevProgram* p;
+        rc = get_program(c, key, pc.La, pc.Lb, 0, sph, normalize, &p);
+        if (rc) return rc;
+        size_t smem = 0;
+        cudaStream_t s;
+        rc = fan.stream(&s);
+        if (rc) return rc;
+        if (key == SI_COUL) {
+            int nw = pick_warps(c, p->dev, 8, &smem);
+            if (nw < 1) return SI_ERR_INTERNAL;
+            int grid = std::min(pc.n, c->sm_count * 16);
+            k_coul<<<grid, nw * 32, smem, s>>>(p->dev, c->boys_dev, bd, pc.d_items, pc.n, d_cxyz, d_q, ncharge, od);
+        } else {
+            int nw = pick_warps(c, p->dev, 4, &smem);
+            if (nw < 1) return SI_ERR_INTERNAL;
+            int grid = std::min((pc.n + nw - 1) / nw, c->sm_count * 16);
+            int* counter = c->d_counters + (c->next_counter++ % SI_NCOUNTERS);
+            k_two_index<<<grid, nw * 32, smem, s>>>(p->dev, c->boys_dev, bd, pc.d_items, pc.n, key == SI_2C2E ? 1 : 0,
+                                                    R ? R[0] : 0.0, R ? R[1] : 0.0, R ? R[2] : 0.0, od, counter);
+        }
+        c->launches++;
+        SI_CUDA(cudaGetLastError());
+    }
+    return fan.end();
+}
+
+int si_int1e(si_context* c, const si_basis* b, int key, int sph, int normalize, const double* R, double* out_dev,
+             void* stream) {
+    if (!c || !b || !out_dev) return SI_ERR_ARG;
+    if (!check_key_2idx(key)) return SI_ERR_KEY;
+    return run_two_index(c, b, key, sph, normalize, R, 0, nullptr, nullptr, out_dev, (cudaStream_t)stream);
+}
+
+int si_int2c2e(si_context* c, const si_basis* b, int sph, int normalize, double* out_dev, void* stream) {
+    if (!c || !b || !out_dev) return SI_ERR_ARG;
+    return run_two_index(c, b, SI_2C2E, sph, normalize, nullptr, 0, nullptr, nullptr, out_dev, (cudaStream_t)stream);
+}
+
+int si_coul(si_context* c, const si_basis* b, int sph, int normalize, int ncharge, const double* xyz, const double* q,
+            double* out_dev, void* stream) {
+    if (!c || !b || !out_dev || ncharge <= 0 || !xyz || !q) return SI_ERR_ARG;
+    SI_CUDA(cudaSetDevice(c->device));
+    double *dx = nullptr, *dq = nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    SI_CUDA(cudaMallocAsync((void**)&dx, (size_t)ncharge * 3 * sizeof(double), s));
+    SI_CUDA(cudaMallocAsync((void**)&dq, (size_t)ncharge * sizeof(double), s));
+    SI_CUDA(cudaMemcpyAsync(dx, xyz, (size_t)ncharge * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    SI_CUDA(cudaMemcpyAsync(dq, q, (size_t)ncharge * sizeof(double), cudaMemcpyHostToDevice, s));
+    int rc = run_two_index(c, b, SI_COUL, sph, normalize, nullptr, ncharge, dx, dq, out_dev, s);
+    cudaFreeAsync(dx, s);
+    cudaFreeAsync(dq, s);
+    return rc;
+}
+
+int si_int3c2e(si_context* c, const si_basis* corb, const si_basis* caux, int sb, int se, int normalize, int layout,
+               double* out_dev, size_t out_len, void* stream) {
+    if (!c || !corb || !caux || !out_dev) return SI_ERR_ARG;
+    si_basis* orb = const_cast<si_basis*>(corb);
+    const si_basis* aux = caux;
+    if (sb < 0 || se > aux->nshell || sb >= se) return SI_ERR_ARG;
+    if (orb->lmax > c->lmax || aux->lmax > c->lauxmax) return SI_ERR_LMAX;
+    SI_CUDA(cudaSetDevice(c->device));
+    int rc = build_pair_classes(orb);
+    if (rc) return rc;
+    const int col_begin = aux->foff_sph[sb];
+    const int col_end = (se == aux->nshell) ? aux->nbf_sph : aux->foff_sph[se];
+    const long long naux_local = col_end - col_begin;
+    const long long rows = (layout == SI_LAYOUT_FULL) ? (long long)orb->nbf_sph * orb->nbf_sph : orb->packed_rows;
+    if ((unsigned long long)(rows * naux_local) > out_len) {
+        g_last_error = "output buffer too small";
+        return SI_ERR_ARG;
+    }
+    OutDesc od;
+    od.out = out_dev;
+    od.ld = naux_local;
+    od.comp_stride = 0;
+    od.nbf = orb->nbf_sph;
+    od.mode = (layout == SI_LAYOUT_FULL) ? STORE_3C_FULL : STORE_3C_PACKED;
+    cudaStream_t user = (cudaStream_t)stream;
+    // aux shells of the range by angular momentum
+    std::map<int, std::vector<int>> by_l;
+    for (int s = sb; s < se; ++s) by_l[aux->L[s]].push_back(s);
+    std::vector<int> flat;
+    std::map<int, std::pair<int, int>> span;
+    for (auto& kv : by_l) {
+        span[kv.first] = {(int)flat.size(), (int)kv.second.size()};
+        flat.insert(flat.end(), kv.second.begin(), kv.second.end());
+    }
+    int* d_list = nullptr;
+    SI_CUDA(cudaMallocAsync((void**)&d_list, flat.size() * sizeof(int), user));
+    SI_CUDA(cudaMemcpyAsync(d_list, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, user));
+    BasisDev od_orb = basis_dev(orb, 1, normalize);
+    BasisDev od_aux = basis_dev(aux, 1, normalize);
+    Fan fan{c, user};
+    rc = fan.begin();
+    if (rc) return rc;
+    // heaviest classes first
+    struct Job {
+        const si_basis::PairClass* pc;
+        int Lc;
+        double cost;
+    };
+    std::vector<Job> jobs;
+    for (auto& pc : orb->pair_classes)
+        for (auto& kv : span) {
+            DevProgram* p;
+            rc = get_program(c, SI_3C2E, pc.La, pc.Lb, kv.first, 1, normalize, &p);
+            if (rc) return rc;
+            double cost = (double)(p->host.n_fma_prim + p->host.n_fma_contr) * pc.n * kv.second.second;
+            jobs.push_back({&pc, kv.first, cost});
+        }
+    std::sort(jobs.begin(), jobs.end(), [](const Job& a, const Job& b) { return a.cost > b.cost; });
+    for (auto& job : jobs) {
+        DevProgram* p;
+        rc = get_program(c, SI_3C2E, job.pc->La, job.pc->Lb, job.Lc, 1, normalize, &p);
+        if (rc) return rc;
+        size_t smem = 0;
+        int nw = pick_warps(c, p->dev, 4, &smem);
+        if (nw < 1) {
+            g_last_error = "class does not fit into shared memory";
+            return SI_ERR_INTERNAL;
+        }
+        auto sp = span[job.Lc];
+        long long nitems = (long long)job.pc->n * sp.second;
+        int grid = (int)std::min<long long>((nitems + nw - 1) / nw, (long long)c->sm_count * 16);
+        cudaStream_t s;
+        rc = fan.stream(&s);
+        if (rc) return rc;
+        int* counter = c->d_counters + (c->next_counter++ % SI_NCOUNTERS);
+        k_3c2e<<<grid, nw * 32, smem, s>>>(p->dev, c->boys_dev, od_orb, od_aux, job.pc->d_items, job.pc->n,
+                                           d_list + sp.first, sp.second, col_begin, od, counter);
+        c->launches++;
+        SI_CUDA(cudaGetLastError());
+    }
+    rc = fan.end();
+    cudaFreeAsync(d_list, user);
+    return rc;
+}
+
+// ---- host-buffer variants ---------------------------------------------------
+static int run_host(si_context* c, size_t n, double* out_host, const std::function<int(double*)>& f) {
+    SI_CUDA(cudaSetDevice(c->device));
+    double* d = nullptr;
+    SI_CUDA(cudaMalloc((void**)&d, n * sizeof(double)));
+    SI_CUDA(cudaMemset(d, 0, n * sizeof(double)));
+    int rc = f(d);
+    if (rc == SI_OK) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpy(out_host, d, n * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            g_last_error = cudaGetErrorString(e);
+            rc = SI_ERR_CUDA;
+        }
+    }
+    cudaFree(d);
+    return rc;
+}
+
+int si_int1e_h(si_context* c, const si_basis* b, int key, int sph, int normalize, const double* R, double* out) {
+    if (!c || !b || !out) return SI_ERR_ARG;
+    if (!check_key_2idx(key)) return SI_ERR_KEY;
+    size_t nbf = sph ? b->nbf_sph : b->nbf_cart;
+    return run_host(c, nbf * nbf * si_ncomp(key), out,
+                    [&](double* d) { return si_int1e(c, b, key, sph, normalize, R, d, nullptr); });
+}
+int si_coul_h(si_context* c, const si_basis* b, int sph, int normalize, int ncharge, const double* xyz,
+              const double* q, double* out) {
+    if (!c || !b || !out) return SI_ERR_ARG;
+    size_t nbf = sph ? b->nbf_sph : b->nbf_cart;
+    return run_host(c, nbf * nbf, out, [&](double* d) { return si_coul(c, b, sph, normalize, ncharge, xyz, q, d, nullptr); });
+}
+int si_int2c2e_h(si_context* c, const si_basis* b, int sph, int normalize, double* out) {
+    if (!c || !b || !out) return SI_ERR_ARG;
+    size_t nbf = sph ? b->nbf_sph : b->nbf_cart;
+    return run_host(c, nbf * nbf, out, [&](double* d) { return si_int2c2e(c, b, sph, normalize, d, nullptr); });
+}
+int si_int3c2e_h(si_context* c, const si_basis* orb, const si_basis* aux, int sb, int se, int normalize, int layout,
+                 double* out, size_t out_len) {
+    if (!c || !orb || !aux || !out) return SI_ERR_ARG;
+    return run_host(c, out_len, out,
+                    [&](double* d) { return si_int3c2e(c, orb, aux, sb, se, normalize, layout, d, out_len, nullptr); });
+}
+
+// ---- single block with the generated-function signature ---------------------
+int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int normalize, int Ka, const double* ax,
+                  const double* da, const double* A, int Kb, const double* bx, const double* db, const double* B,
+                  int Kc, const double* cx, const double* dc, const double* C, const double* R, double* result) {
+    if (!c || !ax || !da || !A || !bx || !db || !B || !result || Ka <= 0 || Kb <= 0) return SI_ERR_ARG;
+    if (key < 0 || key > SI_3C2E) return SI_ERR_KEY;
+    const bool three = (key == SI_3C2E);
+    if (three && (!cx || !dc || !C || Kc <= 0)) return SI_ERR_ARG;
+    if (three) sph = 1;
+    const int lim = (key == SI_2C2E) ? c->lauxmax : c->lmax;
+    if (La < 0 || Lb < 0 || La > lim || Lb > lim || (three && (Lc < 0 || Lc > c->lauxmax))) return SI_ERR_LMAX;
+    SI_CUDA(cudaSetDevice(c->device));
+    const bool swap = La < Lb;
+    // orbital "basis" of two shells (a = higher L first)
+    int Ls[2] = {swap ? Lb : La, swap ? La : Lb};
+    int nps[2] = {swap ? Kb : Ka, swap ? Ka : Kb};
+    std::vector<double> cen(6), ex, co;
+    const double* A_ = swap ? B : A;
+    const double* B_ = swap ? A : B;
+    for (int d = 0; d < 3; ++d) {
+        cen[d] = A_[d];
+        cen[3 + d] = B_[d];
+    }
+    ex.insert(ex.end(), swap ? bx : ax, (swap ? bx : ax) + nps[0]);
+    ex.insert(ex.end(), swap ? ax : bx, (swap ? ax : bx) + nps[1]);
+    co.insert(co.end(), swap ? db : da, (swap ? db : da) + nps[0]);
+    co.insert(co.end(), swap ? da : db, (swap ? da : db) + nps[1]);
+    si_basis* ob = nullptr;
+    int rc = si_basis_create(c, 2, Ls, nps, cen.data(), ex.data(), co.data(), &ob);
+    if (rc) return rc;
+    si_basis* xb = nullptr;
+    if (three) {
+        rc = si_basis_create(c, 1, &Lc, &Kc, C, cx, dc, &xb);
+        if (rc) {
+            si_basis_destroy(ob);
+            return rc;
+        }
+    }
+    DevProgram* p;
+    rc = get_program(c, key, Ls[0], Ls[1], three ? Lc : 0, sph, normalize, &p);
+    if (rc) {
+        si_basis_destroy(ob);
+        if (xb) si_basis_destroy(xb);
+        return rc;
+    }
+    const SiProg& P = p->dev;
+    const int n = P.out_n0 * P.out_n1 * P.nb_total;
+    double* d_out = nullptr;
+    SiPairItem item;
+    memset(&item, 0, sizeof(item));
+    item.sa = 0;
+    item.sb = 1;
+    SiPairItem* d_item = nullptr;
+    int* d_counter = nullptr;
+    double *d_R = nullptr, *d_q = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_out, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_item, sizeof(item));
+    if (e == cudaSuccess) e = cudaMemcpy(d_item, &item, sizeof(item), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_counter, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(d_counter, 0, sizeof(int));
+    OutDesc od;
+    od.out = d_out;
+    od.ld = 0;
+    od.comp_stride = 0;
+    od.nbf = 0;
+    od.mode = STORE_BLOCK;
+    size_t smem = 0;
+    int nw = pick_warps(c, P, 1, &smem);
+    if (e == cudaSuccess && nw >= 1) {
+        BasisDev bd = basis_dev(ob, sph, normalize);
+        bd.foff = nullptr;
+        if (three) {
+            BasisDev ad = basis_dev(xb, 1, normalize);
+            k_3c2e<<<1, 32, smem>>>(P, c->boys_dev, bd, ad, d_item, 1, nullptr, 1, 0, od, d_counter);
+        } else if (key == SI_COUL) {
+            double one = 1.0;
+            double Rz[3] = {R ? R[0] : 0.0, R ? R[1] : 0.0, R ? R[2] : 0.0};
+            e = cudaMalloc((void**)&d_R, 3 * sizeof(double));
+            if (e == cudaSuccess) e = cudaMalloc((void**)&d_q, sizeof(double));
+            if (e == cudaSuccess) e = cudaMemcpy(d_R, Rz, 3 * sizeof(double), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(d_q, &one, sizeof(double), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) k_coul<<<1, 32, smem>>>(P, c->boys_dev, bd, d_item, 1, d_R, d_q, 1, od);
+        } else {
+            k_two_index<<<1, 32, smem>>>(P, c->boys_dev, bd, d_item, 1, key == SI_2C2E ? 1 : 0, R ? R[0] : 0.0,
+                                         R ? R[1] : 0.0, R ? R[2] : 0.0, od, d_counter);
+        }
+        c->launches++;
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    std::vector<double> tmp(n);
+    if (e == cudaSuccess) e = cudaMemcpy(tmp.data(), d_out, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    cudaFree(d_item);
+    cudaFree(d_counter);
+    cudaFree(d_R);
+    cudaFree(d_q);
+    si_basis_destroy(ob);
+    if (xb) si_basis_destroy(xb);
+    if (nw < 1) return SI_ERR_INTERNAL;
+    if (e != cudaSuccess) {
+        g_last_error = cudaGetErrorString(e);
+        return SI_ERR_CUDA;
+    }
+    if (!swap) {
+        memcpy(result, tmp.data(), n * sizeof(double));
+    } else {
+        // computed (comp, b, a[, c]) -> (comp, a, b[, c])   (resort_ba_ab / resort_bac_abc)
+        const int nb_ = P.out_n0, na_ = P.out_n1;  // computed block is (n0 = size of Lb-shell..)
+        const int ncomp = P.out_batch_major ? P.nb_total : 1;
+        const int nc = P.out_batch_major ? 1 : P.nb_total;
+        for (int q = 0; q < ncomp; ++q)
+            for (int ib = 0; ib < nb_; ++ib)
+                for (int ia = 0; ia < na_; ++ia)
+                    for (int m = 0; m < nc; ++m)
+                        result[((size_t)(q * na_ + ia) * nb_ + ib) * nc + m] =
+                            tmp[((size_t)(q * nb_ + ib) * na_ + ia) * nc + m];
+    }
+    return SI_OK;
+}

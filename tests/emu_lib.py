@@ -1,0 +1,92 @@
+"""ctypes access to the TEST-ONLY host emulator (tests/emu/libsi_emu.so)."""
+import ctypes
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REPO = HERE.parent
+KEYS = {"ovlp": 0, "kin": 1, "dpm": 2, "qpm": 3, "dqpm": 4, "coul": 5, "2c2e": 6, "3c2e": 7}
+NCOMP = {"ovlp": 1, "kin": 1, "dpm": 3, "qpm": 6, "dqpm": 3, "coul": 1, "2c2e": 1, "3c2e": 1}
+NORM = {"none": 0, "cgto": 1, "pgto": 2}
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def build_emu(force=False):
+    so = HERE / "emu" / "libsi_emu.so"
+    srcs = [HERE / "emu" / "si_emu.cpp", REPO / "sympleints_b200" / "csrc" / "si_program.cpp"]
+    hdrs = [REPO / "sympleints_b200" / "csrc" / "si_machine.h", REPO / "sympleints_b200" / "csrc" / "si_program.h"]
+    newest = max(p.stat().st_mtime for p in srcs + hdrs)
+    if force or not so.exists() or so.stat().st_mtime < newest:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(so)] + [str(s) for s in srcs])
+    return so
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(str(build_emu()))
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def xlarge_pref(nmax):
+    from math import pi, sqrt
+    out = np.empty(nmax + 1)
+    for n in range(nmax + 1):
+        f2 = 1.0
+        k = 2 * n - 1
+        while k > 1:
+            f2 *= k
+            k -= 2
+        out[n] = f2 / 2 ** (n + 1) * sqrt(pi)
+    return out
+
+
+def program_stats(key, La, Lb, Lc=0, sph=True, normalize="cgto"):
+    out = (ctypes.c_longlong * 8)()
+    rc = lib().siemu_program_stats(KEYS[key], La, Lb, Lc, int(sph), NORM[normalize], out)
+    assert rc == 0
+    names = ["w_size", "nstages", "n_fma_prim", "n_fma_contr", "lut_words", "nconst", "chunk", "x_size"]
+    return dict(zip(names, list(out)))
+
+
+def emu_eval(key, La, Lb, Lc, shell_a, shell_b, shell_c=None, R=None, q=None, sph=True, normalize="cgto", table=None):
+    """shell_* = (exps, coeffs, center).  Handles La < Lb by swapping + transposing."""
+    if La < Lb:
+        res = emu_eval(key, Lb, La, Lc, shell_b, shell_a, shell_c, R, q, sph, normalize, table)
+        size = (lambda l: 2 * l + 1) if (sph or key == "3c2e") else (lambda l: (l + 1) * (l + 2) // 2)
+        na, nb = size(La), size(Lb)
+        ncomp = NCOMP[key]
+        nc = res.size // (ncomp * na * nb)
+        return res.reshape(ncomp, nb, na, nc).transpose(0, 2, 1, 3).ravel().copy()
+    if table is None:
+        from oracle import boys as oboys
+        table = oboys.table()
+    table = np.ascontiguousarray(table)
+    pref = xlarge_pref(table.shape[0] - 7)
+    ax, da, A = [np.ascontiguousarray(x, dtype=float) for x in shell_a]
+    bx, db, B = [np.ascontiguousarray(x, dtype=float) for x in shell_b]
+    if shell_c is not None:
+        cx, dc, C = [np.ascontiguousarray(x, dtype=float) for x in shell_c]
+    else:
+        cx, dc, C = np.ones(1), np.ones(1), np.zeros(3)
+    R = np.zeros(3) if R is None else np.ascontiguousarray(R, dtype=float).reshape(-1)
+    ncharge = R.size // 3
+    q = np.ones(ncharge) if q is None else np.ascontiguousarray(q, dtype=float)
+    size = (lambda l: 2 * l + 1) if (sph or key == "3c2e") else (lambda l: (l + 1) * (l + 2) // 2)
+    n = NCOMP[key] * size(La) * size(Lb) * (2 * Lc + 1 if key == "3c2e" else 1)
+    res = np.zeros(n)
+    rc = lib().siemu_eval(
+        KEYS[key], La, Lb, Lc, int(sph), NORM[normalize],
+        ax.size, _p(ax), _p(da), _p(A), bx.size, _p(bx), _p(db), _p(B), cx.size, _p(cx), _p(dc), _p(C),
+        _p(R), ncharge, _p(q), _p(table), table.shape[0], table.shape[1], _p(pref), _p(res))
+    assert rc == 0
+    return res
