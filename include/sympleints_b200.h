@@ -144,6 +144,9 @@ int si_eval_block(si_context* ctx, int key, int La, int Lb, int Lc, int sph, int
                   const double* db, const double* B, int Kc, const double* cx, const double* dc,
                   const double* C, const double* R, double* result);
 
+/* Measured FP64 FMA peak of the device (TFLOP/s, best of several launches over ~`seconds`):
+ * the roofline denominator for the Boys-type kernels. */
+int si_fp64_peak(si_context* ctx, double seconds, double* tflops);
 /* Bookkeeping for benchmarks: kernels launched by this context since creation. */
 long long si_launch_count(const si_context* ctx);
 /*

@@ -65,8 +65,8 @@ __device__ __forceinline__ void load_consts(const SiProg& P, double* S, int lane
     for (int c = lane; c < P.nconst; c += 32) S[SI_NDYN + c] = P.consts[c];
 }
 
-__device__ __forceinline__ void contracted_phase(const SiProg& P, double* W, double* S, const double* A,
-                                                 const double* B, int lane) {
+__device__ __forceinline__ void contracted_phase(const SiProg& P, const SiStage* stg, double* W, double* S,
+                                                 const double* A, const double* B, int lane) {
     auto sync = [] { __syncwarp(); };
     __syncwarp();
     {
@@ -79,10 +79,10 @@ __device__ __forceinline__ void contracted_phase(const SiProg& P, double* W, dou
         for (int d = 0; d < 3; ++d) v[6 + d] = A[d] - B[d];
         si_fill_scalars(S, v, kb, 0.0, lane, 32);
     }
-    si_run_stages(P, P.n_prim_stages, P.chunk_begin, W, S, 0, 1, lane, 32, sync);
+    si_run_stages(P, stg, P.n_prim_stages, P.chunk_begin, W, S, 0, 1, lane, 32, sync);
     for (int m0 = 0; m0 < P.nb_total; m0 += P.chunk) {
         const int nb = min(P.chunk, P.nb_total - m0);
-        si_run_stages(P, P.chunk_begin, P.nstages, W, S, m0, nb, lane, 32, sync);
+        si_run_stages(P, stg, P.chunk_begin, P.nstages, W, S, m0, nb, lane, 32, sync);
     }
     __syncwarp();
 }
@@ -127,9 +127,17 @@ __global__ void __launch_bounds__(256) k_two_index(SiProg P, SiBoys Bt, BasisDev
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (P.w_size + SI_NDYN + P.nconst + 1) & ~1;
-    double* W = smem + (size_t)warp * per;
+    SiStage* stg = reinterpret_cast<SiStage*>(smem);
+    const int stg_doubles = (P.nstages * (int)sizeof(SiStage) + 7) / 8;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.stages);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+        for (int i = threadIdx.x; i < P.nstages * (int)(sizeof(SiStage) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    double* W = smem + stg_doubles + (size_t)warp * per;
     double* S = W + P.w_size;
     load_consts(P, S, lane);
+    __syncthreads();
     auto sync = [] { __syncwarp(); };
     const double R[3] = {Rx, Ry, Rz};
     for (long long item = next_item(counter, lane); item < nitems; item = next_item(counter, lane)) {
@@ -153,10 +161,10 @@ __global__ void __launch_bounds__(256) k_two_index(SiProg P, SiBoys Bt, BasisDev
                     si_setup_2c2e(P, Bt, ax, da, A, bx, db, B, W, S, lane, 32);
                 else
                     si_setup_1e(P, ax, da, A, bx, db, B, R, W, S, lane, 32);
-                si_run_stages(P, 0, P.n_prim_stages, W, S, 0, 1, lane, 32, sync);
+                si_run_stages(P, stg, 0, P.n_prim_stages, W, S, 0, 1, lane, 32, sync);
             }
         }
-        contracted_phase(P, W, S, A, B, lane);
+        contracted_phase(P, stg, W, S, A, B, lane);
         store_matrix(P, W, od, bs.foff ? bs.foff[it.sa] : 0, bs.foff ? bs.foff[it.sb] : 0, it.sa == it.sb, lane);
     }
 }
@@ -169,9 +177,17 @@ __global__ void __launch_bounds__(256) k_coul(SiProg P, SiBoys Bt, BasisDev bs, 
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const int per = (P.w_size + SI_NDYN + P.nconst + 1) & ~1;
-    double* W = smem + (size_t)warp * per;
+    SiStage* stg = reinterpret_cast<SiStage*>(smem);
+    const int stg_doubles = (P.nstages * (int)sizeof(SiStage) + 7) / 8;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.stages);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+        for (int i = threadIdx.x; i < P.nstages * (int)(sizeof(SiStage) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    double* W = smem + stg_doubles + (size_t)warp * per;
     double* S = W + P.w_size;
     load_consts(P, S, lane);
+    __syncthreads();
     auto sync = [] { __syncwarp(); };
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const SiPairItem it = items[item];
@@ -193,20 +209,21 @@ __global__ void __launch_bounds__(256) k_coul(SiProg P, SiBoys Bt, BasisDev bs, 
                     const double Rc[3] = {cxyz[3 * c], cxyz[3 * c + 1], cxyz[3 * c + 2]};
                     __syncwarp();
                     si_setup_coul(P, Bt, ax, da, A, bx, db, B, Rc, cq[c], W, S, lane, 32);
-                    si_run_stages(P, 0, P.n_prim_stages, W, S, 0, 1, lane, 32, sync);
+                    si_run_stages(P, stg, 0, P.n_prim_stages, W, S, 0, 1, lane, 32, sync);
                 }
             }
         }
         __syncthreads();
         // reduce the per-warp accumulators into warp 0's X (fixed order: deterministic)
         for (int i = threadIdx.x; i < P.x_size; i += blockDim.x) {
-            double s = smem[P.x_off + i];
-            for (int w = 1; w < nw; ++w) s += smem[(size_t)w * per + P.x_off + i];
-            smem[P.x_off + i] = s;
+            double* base = smem + stg_doubles;
+            double s = base[P.x_off + i];
+            for (int w = 1; w < nw; ++w) s += base[(size_t)w * per + P.x_off + i];
+            base[P.x_off + i] = s;
         }
         __syncthreads();
         if (warp == 0) {
-            contracted_phase(P, W, S, A, B, lane);
+            contracted_phase(P, stg, W, S, A, B, lane);
             store_matrix(P, W, od, bs.foff ? bs.foff[it.sa] : 0, bs.foff ? bs.foff[it.sb] : 0, it.sa == it.sb,
                          lane);
         }
@@ -220,9 +237,17 @@ __global__ void __launch_bounds__(256) k_3c2e(SiProg P, SiBoys Bt, BasisDev orb,
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (P.w_size + SI_NDYN + P.nconst + 1) & ~1;
-    double* W = smem + (size_t)warp * per;
+    SiStage* stg = reinterpret_cast<SiStage*>(smem);
+    const int stg_doubles = (P.nstages * (int)sizeof(SiStage) + 7) / 8;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.stages);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+        for (int i = threadIdx.x; i < P.nstages * (int)(sizeof(SiStage) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    double* W = smem + stg_doubles + (size_t)warp * per;
     double* S = W + P.w_size;
     load_consts(P, S, lane);
+    __syncthreads();
     auto sync = [] { __syncwarp(); };
     const long long nitems = (long long)npairs * naux_c;
     for (long long item = next_item(counter, lane); item < nitems; item = next_item(counter, lane)) {
@@ -249,11 +274,11 @@ __global__ void __launch_bounds__(256) k_3c2e(SiProg P, SiBoys Bt, BasisDev orb,
                     const double cx = aux.exps[pc + k], dc = aux.coef[pc + k];
                     __syncwarp();
                     si_setup_3c2e(P, Bt, ax, da, A, bx, db, B, cx, dc, C, W, S, lane, 32);
-                    si_run_stages(P, 0, P.n_prim_stages, W, S, 0, 1, lane, 32, sync);
+                    si_run_stages(P, stg, 0, P.n_prim_stages, W, S, 0, 1, lane, 32, sync);
                 }
             }
         }
-        contracted_phase(P, W, S, A, B, lane);
+        contracted_phase(P, stg, W, S, A, B, lane);
         // store: W[out_off + (i*n1 + j)*nm + m]
         const int n0 = P.out_n0, n1 = P.out_n1, nm = P.nb_total;
         const int total = n0 * n1 * nm;
@@ -744,9 +769,10 @@ struct Fan {
 
 static int pick_warps(const si_context* c, const SiProg& P, int max_warps, size_t* smem_bytes) {
     const size_t per = (size_t)((P.w_size + SI_NDYN + P.nconst + 1) & ~1) * sizeof(double);
-    int nw = (int)std::min<size_t>((size_t)max_warps, (size_t)c->max_smem / per);
+    const size_t stg = (size_t)((P.nstages * sizeof(SiStage) + 7) / 8) * sizeof(double);
+    int nw = (int)std::min<size_t>((size_t)max_warps, ((size_t)c->max_smem - stg) / per);
     if (nw < 1) return 0;
-    *smem_bytes = per * nw;
+    *smem_bytes = stg + per * nw;
     return nw;
 }
 
@@ -953,11 +979,132 @@ int si_int2c2e_h(si_context* c, const si_basis* b, int sph, int normalize, doubl
     size_t nbf = sph ? b->nbf_sph : b->nbf_cart;
     return run_host(c, nbf * nbf, out, [&](double* d) { return si_int2c2e(c, b, sph, normalize, d, nullptr); });
 }
+// Host-buffer 3c2e: the aux-shell range is cut into chunks; each chunk is computed into one of two
+// device staging buffers and copied to its column range of the host tensor with cudaMemcpy2DAsync on
+// a copy stream while the next chunk computes (the host buffer should be pinned for full overlap).
 int si_int3c2e_h(si_context* c, const si_basis* orb, const si_basis* aux, int sb, int se, int normalize, int layout,
                  double* out, size_t out_len) {
     if (!c || !orb || !aux || !out) return SI_ERR_ARG;
-    return run_host(c, out_len, out,
-                    [&](double* d) { return si_int3c2e(c, orb, aux, sb, se, normalize, layout, d, out_len, nullptr); });
+    if (sb < 0 || se > aux->nshell || sb >= se) return SI_ERR_ARG;
+    SI_CUDA(cudaSetDevice(c->device));
+    const long long rows = (layout == SI_LAYOUT_FULL) ? (long long)orb->nbf_sph * orb->nbf_sph : orb->packed_rows;
+    const int col_begin = aux->foff_sph[sb];
+    const int col_end = (se == aux->nshell) ? aux->nbf_sph : aux->foff_sph[se];
+    const long long ncol = col_end - col_begin;
+    if ((unsigned long long)(rows * ncol) > out_len) {
+        g_last_error = "output buffer too small";
+        return SI_ERR_ARG;
+    }
+    // chunk boundaries: ~equal numbers of columns, at most 1 GiB of staging per buffer
+    const long long max_cols = std::max<long long>(1, (1ll << 30) / (rows * 8));
+    const long long want = std::max<long long>(1, std::min<long long>(max_cols, (ncol + 7) / 8));
+    std::vector<int> cuts;
+    cuts.push_back(sb);
+    long long acc = 0;
+    for (int s = sb; s < se; ++s) {
+        acc += si_nsph(aux->L[s]);
+        if (acc >= want && s + 1 < se) {
+            cuts.push_back(s + 1);
+            acc = 0;
+        }
+    }
+    cuts.push_back(se);
+    long long maxc = 0;
+    for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+        int e = cuts[k + 1];
+        long long cc = ((e == aux->nshell) ? aux->nbf_sph : aux->foff_sph[e]) - aux->foff_sph[cuts[k]];
+        maxc = std::max(maxc, cc);
+    }
+    double* stage[2] = {nullptr, nullptr};
+    cudaStream_t s_comp, s_copy;
+    cudaEvent_t ev_done[2], ev_free[2];
+    SI_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+    SI_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        SI_CUDA(cudaMalloc((void**)&stage[i], (size_t)rows * maxc * sizeof(double)));
+        SI_CUDA(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+        SI_CUDA(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
+    }
+    int rc = SI_OK;
+    for (size_t k = 0; k + 1 < cuts.size() && rc == SI_OK; ++k) {
+        const int b = (int)(k & 1);
+        const int cs = cuts[k], ce = cuts[k + 1];
+        const long long c0 = aux->foff_sph[cs] - col_begin;
+        const long long cc = ((ce == aux->nshell) ? aux->nbf_sph : aux->foff_sph[ce]) - aux->foff_sph[cs];
+        if (k >= 2) SI_CUDA(cudaStreamWaitEvent(s_comp, ev_free[b], 0));
+        rc = si_int3c2e(c, orb, aux, cs, ce, normalize, layout, stage[b], (size_t)(rows * cc), (void*)s_comp);
+        if (rc != SI_OK) break;
+        SI_CUDA(cudaEventRecord(ev_done[b], s_comp));
+        SI_CUDA(cudaStreamWaitEvent(s_copy, ev_done[b], 0));
+        SI_CUDA(cudaMemcpy2DAsync(out + c0, (size_t)ncol * sizeof(double), stage[b], (size_t)cc * sizeof(double),
+                                  (size_t)cc * sizeof(double), (size_t)rows, cudaMemcpyDeviceToHost, s_copy));
+        SI_CUDA(cudaEventRecord(ev_free[b], s_copy));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(s_comp);
+    cudaError_t e2 = cudaStreamSynchronize(s_copy);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(stage[i]);
+        cudaEventDestroy(ev_done[i]);
+        cudaEventDestroy(ev_free[i]);
+    }
+    cudaStreamDestroy(s_comp);
+    cudaStreamDestroy(s_copy);
+    if (rc == SI_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+        g_last_error = cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);
+        rc = SI_ERR_CUDA;
+    }
+    return rc;
+}
+
+// ---- FP64 peak microbenchmark (roofline denominator; not in MEASURED_PEAKS.json) ------------------
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c);
+            a1 = fma(a1, m, c);
+            a2 = fma(a2, m, c);
+            a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c);
+            a5 = fma(a5, m, c);
+            a6 = fma(a6, m, c);
+            a7 = fma(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int si_fp64_peak(si_context* c, double seconds, double* tflops) {
+    if (!c || !tflops) return SI_ERR_ARG;
+    SI_CUDA(cudaSetDevice(c->device));
+    const int blocks = c->sm_count * 8, threads = 256;
+    double* d = nullptr;
+    SI_CUDA(cudaMalloc((void**)&d, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    SI_CUDA(cudaEventCreate(&e0));
+    SI_CUDA(cudaEventCreate(&e1));
+    int iters = 2000;
+    double best = 0.0, spent = 0.0;
+    for (int rep = 0; rep < 50 && spent < seconds; ++rep) {
+        SI_CUDA(cudaEventRecord(e0));
+        k_dfma_peak<<<blocks, threads>>>(d, iters);
+        SI_CUDA(cudaEventRecord(e1));
+        SI_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        SI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        spent += ms * 1e-3;
+        if (ms < 20.0f) iters *= 2;
+    }
+    c->launches += 1;
+    cudaFree(d);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return SI_OK;
 }
 
 // ---- single block with the generated-function signature ---------------------

@@ -78,50 +78,78 @@ struct SiProg {
 };
 
 // Execute stages [s0, s1) for batch indices [m0, m0+nb).
+// Each lane works on SI_UNROLL independent elements at a time so that the look-up-table loads,
+// the shared-memory operand loads and the FMAs of different elements overlap.
+#ifndef SI_UNROLL
+#define SI_UNROLL 1
+#endif
 template <typename SyncF>
-SI_HD void si_run_stages(const SiProg& P, int s0, int s1, double* W, const double* S,
+SI_HD void si_run_stages(const SiProg& P, const SiStage* stages, int s0, int s1, double* W, const double* S,
                          int m0, int nb, int lane, int nlanes, SyncF sync) {
     for (int s = s0; s < s1; ++s) {
-        const SiStage st = P.stages[s];
+        const SiStage st = stages[s];
         if (st.flags & SI_ST_SYNC) sync();
         const int nbb = st.nb_fixed > 0 ? st.nb_fixed : (st.batched ? nb : 1);
         const int total = st.nelem * nbb;
         const uint32_t* hdr = P.hdr + st.hdr_off;
         const uint32_t* trm = P.terms + st.term_off;
         const int soff = st.scs * m0, doff = st.dcs * m0;
-        for (int e = lane; e < total; e += nlanes) {
-            int b = 0, el = e;
-            if (nbb > 1 && st.nelem == 1) {
-                b = e;
-                el = 0;
-            } else if (nbb > 1) {
+        const int nelem = st.nelem, nterms = st.nterms;
+        for (int e0 = lane; e0 < total; e0 += nlanes * SI_UNROLL) {
+            int el[SI_UNROLL], sb[SI_UNROLL], db[SI_UNROLL];
+            bool ok[SI_UNROLL];
+            double acc[SI_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SI_UNROLL; ++u) {
+                int e = e0 + u * nlanes;
+                ok[u] = e < total;
+                if (!ok[u]) e = e0;
+                int b = 0, x = e;
+                if (nbb > 1 && nelem == 1) {
+                    b = e;
+                    x = 0;
+                } else if (nbb > 1) {
 #if defined(__CUDA_ARCH__)
-                b = (int)__umulhi((uint32_t)e, st.magic);
+                    b = (int)__umulhi((uint32_t)e, st.magic);
 #else
-                b = (int)(((uint64_t)(uint32_t)e * st.magic) >> 32);
+                    b = (int)(((uint64_t)(uint32_t)e * st.magic) >> 32);
 #endif
-                el = e - b * st.nelem;
+                    x = e - b * nelem;
+                }
+                el[u] = x;
+                sb[u] = soff + b * st.sbs;
+                db[u] = doff + b * st.dbs;
+                acc[u] = 0.0;
             }
-            const int sb = soff + b * st.sbs;
-            double acc = 0.0;
             if (st.flags & SI_ST_PROD3) {
-                for (int k = 0; k < st.nterms; k += 3) {
-                    uint32_t t0 = trm[(k + 0) * st.nelem + el];
-                    uint32_t t1 = trm[(k + 1) * st.nelem + el];
-                    uint32_t t2 = trm[(k + 2) * st.nelem + el];
-                    acc += W[(t0 & 0xffffu)] * W[(t1 & 0xffffu)] * W[(t2 & 0xffffu)];
+                for (int k = 0; k < nterms; k += 3) {
+#pragma unroll
+                    for (int u = 0; u < SI_UNROLL; ++u) {
+                        uint32_t t0 = trm[(k + 0) * nelem + el[u]];
+                        uint32_t t1 = trm[(k + 1) * nelem + el[u]];
+                        uint32_t t2 = trm[(k + 2) * nelem + el[u]];
+                        acc[u] += W[(t0 & 0xffffu)] * W[(t1 & 0xffffu)] * W[(t2 & 0xffffu)];
+                    }
                 }
             } else {
-                for (int k = 0; k < st.nterms; ++k) {
-                    uint32_t t = trm[k * st.nelem + el];
-                    acc += S[t >> 16] * W[(int)(t & 0xffffu) + sb];
+                for (int k = 0; k < nterms; ++k) {
+                    uint32_t t[SI_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < SI_UNROLL; ++u) t[u] = trm[k * nelem + el[u]];
+#pragma unroll
+                    for (int u = 0; u < SI_UNROLL; ++u) acc[u] += S[t[u] >> 16] * W[(int)(t[u] & 0xffffu) + sb[u]];
                 }
             }
-            const int d = (int)hdr[el] + doff + b * st.dbs;
-            if (st.flags & SI_ST_ACCUM)
-                W[d] += acc;
-            else
-                W[d] = acc;
+#pragma unroll
+            for (int u = 0; u < SI_UNROLL; ++u) {
+                if (ok[u]) {
+                    const int d = (int)hdr[el[u]] + db[u];
+                    if (st.flags & SI_ST_ACCUM)
+                        W[d] += acc[u];
+                    else
+                        W[d] = acc[u];
+                }
+            }
         }
     }
 }

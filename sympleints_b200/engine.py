@@ -113,6 +113,11 @@ class Engine:
         check(self.lib.si_boys_eval(self.ctx, int(n), _dp(xs), xs.size, _dp(out)))
         return out
 
+    def fp64_peak(self, seconds=0.5):
+        out = c_double()
+        check(self.lib.si_fp64_peak(self.ctx, float(seconds), ctypes.byref(out)))
+        return out.value
+
     def class_stats(self, key, La, Lb, Lc=0, sph=True, normalize="cgto"):
         out = (c_longlong * 4)()
         check(self.lib.si_class_stats(self.ctx, KEYS[key], La, Lb, Lc, int(sph), NORMALIZE[normalize], out))

@@ -92,20 +92,20 @@ int siemu_eval(int key, int La, int Lb, int Lc, int sph, int normalize, int Ka, 
                     for (int k = 0; k < Kc; ++k) {
                         si_setup_3c2e(P, Bt, ax[i], da[i], A, bx[j], db[j], B, cx[k], dc[k], C, W.data(),
                                       S.data(), 0, 1);
-                        si_run_stages(P, 0, P.n_prim_stages, W.data(), S.data(), 0, 1, 0, 1, nosync);
+                        si_run_stages(P, P.stages, 0, P.n_prim_stages, W.data(), S.data(), 0, 1, 0, 1, nosync);
                     }
                 } else if (key == SI_KEY_COUL) {
                     for (int k = 0; k < ncharge; ++k) {
                         si_setup_coul(P, Bt, ax[i], da[i], A, bx[j], db[j], B, R + 3 * k, q[k], W.data(),
                                       S.data(), 0, 1);
-                        si_run_stages(P, 0, P.n_prim_stages, W.data(), S.data(), 0, 1, 0, 1, nosync);
+                        si_run_stages(P, P.stages, 0, P.n_prim_stages, W.data(), S.data(), 0, 1, 0, 1, nosync);
                     }
                 } else if (key == SI_KEY_2C2E) {
                     si_setup_2c2e(P, Bt, ax[i], da[i], A, bx[j], db[j], B, W.data(), S.data(), 0, 1);
-                    si_run_stages(P, 0, P.n_prim_stages, W.data(), S.data(), 0, 1, 0, 1, nosync);
+                    si_run_stages(P, P.stages, 0, P.n_prim_stages, W.data(), S.data(), 0, 1, 0, 1, nosync);
                 } else {
                     si_setup_1e(P, ax[i], da[i], A, bx[j], db[j], B, R, W.data(), S.data(), 0, 1);
-                    si_run_stages(P, 0, P.n_prim_stages, W.data(), S.data(), 0, 1, 0, 1, nosync);
+                    si_run_stages(P, P.stages, 0, P.n_prim_stages, W.data(), S.data(), 0, 1, 0, 1, nosync);
                 }
             }
         // geometry-only scalars needed by the contracted phase (AB for the HRR)
@@ -114,10 +114,10 @@ int siemu_eval(int key, int La, int Lb, int Lc, int sph, int normalize, int Ka, 
             for (int d = 0; d < 3; ++d) v[6 + d] = A[d] - B[d];
             si_fill_scalars(S.data(), v, kb, 0.0, 0, 1);
         }
-        si_run_stages(P, P.n_prim_stages, P.chunk_begin, W.data(), S.data(), 0, 1, 0, 1, nosync);
+        si_run_stages(P, P.stages, P.n_prim_stages, P.chunk_begin, W.data(), S.data(), 0, 1, 0, 1, nosync);
         for (int m0 = 0; m0 < P.nb_total; m0 += P.chunk) {
             int nb = P.nb_total - m0 < P.chunk ? P.nb_total - m0 : P.chunk;
-            si_run_stages(P, P.chunk_begin, P.nstages, W.data(), S.data(), m0, nb, 0, 1, nosync);
+            si_run_stages(P, P.stages, P.chunk_begin, P.nstages, W.data(), S.data(), m0, nb, 0, 1, nosync);
         }
         int n = P.out_n0 * P.out_n1 * P.nb_total;
         for (int i = 0; i < n; ++i) result[i] = W[P.out_off + i];

@@ -1,0 +1,152 @@
+"""GPU tests of the batched drivers (the counterpart of sympleints/testing/intor.py) on small
+synthetic systems, plus size-independent properties on larger ones."""
+import numpy as np
+import pytest
+
+from oracle import ints
+from sympleints_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _sizes(shells, sph):
+    return [(2 * s.L + 1) if sph else (s.L + 1) * (s.L + 2) // 2 for s in shells]
+
+
+def oracle_matrix(key, shells, sph=True, normalize="cgto", **kw):
+    """intor_2c (testing/intor.py:18-76) driven by the oracle functions."""
+    f, ncomp = ints.KEY_FUNCS[key]
+    off = np.concatenate([[0], np.cumsum(_sizes(shells, sph))])
+    M = np.zeros((ncomp, off[-1], off[-1]))
+    for i, a in enumerate(shells):
+        for j in range(i, len(shells)):
+            b = shells[j]
+            blk = f(a.L, b.L, a.exps, a.coeffs, a.center, b.exps, b.coeffs, b.center, sph=sph,
+                    normalize=normalize, **kw).reshape(ncomp, off[i + 1] - off[i], off[j + 1] - off[j])
+            M[:, off[i]:off[i + 1], off[j]:off[j + 1]] = blk
+            M[:, off[j]:off[j + 1], off[i]:off[i + 1]] = blk.transpose(0, 2, 1)
+    return M
+
+
+@pytest.fixture(scope="module")
+def small(engine):
+    shells, sites = synthetic.orbital_basis(natoms=3, seed=5)
+    aux = synthetic.aux_basis(sites, seed=6)
+    return shells, sites, aux, engine.basis(shells), engine.basis(aux)
+
+
+@pytest.mark.parametrize("key", ["ovlp", "kin", "dpm", "qpm", "dqpm"])
+@pytest.mark.parametrize("sph", [True, False])
+def test_one_electron_matrices(engine, small, key, sph):
+    shells, _, _, ob, _ = small
+    R = np.array([0.3, -0.2, 0.5])
+    g = engine.int1e(key, ob, sph=sph, R=R).cpu().numpy()
+    o = oracle_matrix(key, shells, sph=sph, R=R)
+    g = g.reshape(o.shape)
+    assert np.abs(g - o).max() <= 1e-14 + 1e-12 * np.abs(o).max()
+    # off-diagonal shell blocks are mirrored exactly; diagonal blocks are computed in full
+    assert np.abs(g - g.transpose(0, 2, 1)).max() <= 1e-15 * np.abs(o).max()
+    h = engine.int1e_host(key, ob, sph=sph, R=R).reshape(o.shape)
+    assert np.array_equal(h, g)
+
+
+def test_plumbing_config_ovlp_lmax1(engine):
+    """BASELINE config 1: 20-atom s/p shell set, ovlp, against the intor_2c-style driver."""
+    shells, _ = synthetic.plumbing_basis()
+    assert len(shells) == 60 and sum(_sizes(shells, True)) == 100  # 20 x (s, s, p)
+    b = engine.basis(shells)
+    g = engine.int1e("ovlp", b).cpu().numpy()
+    o = oracle_matrix("ovlp", shells)[0]
+    assert np.abs(g - o).max() <= 1e-14 + 1e-12 * np.abs(o).max()
+    assert np.allclose(np.diag(g), 1.0, atol=1e-13)  # cGTO-normalised shells
+
+
+def test_two_center_two_electron_metric(engine, small):
+    _, _, aux, _, ab = small
+    g = engine.int2c2e(ab).cpu().numpy()
+    o = oracle_matrix("2c2e", aux)[0]
+    assert np.abs(g - o).max() <= 1e-14 + 1e-12 * np.abs(o).max()
+    np.linalg.cholesky(g)  # the metric is positive definite
+
+
+def test_nuclear_attraction_with_point_charges(engine, small):
+    shells, sites, _, ob, _ = small
+    xyz, q = synthetic.point_charges(sites, n=24, seed=3)
+    g = engine.coul(ob, xyz, q).cpu().numpy()
+    o = sum(qq * oracle_matrix("coul", shells, R=rr)[0] for rr, qq in zip(xyz, q))
+    assert np.abs(g - o).max() <= 1e-14 + 1e-12 * np.abs(o).max()
+    h = engine.coul_host(ob, xyz, q)
+    assert np.array_equal(h, g)
+    # linearity in the charges
+    g2 = engine.coul(ob, xyz, 2.0 * q).cpu().numpy()
+    assert np.abs(g2 - 2 * g).max() <= 1e-13 * np.abs(g).max()
+
+
+def _oracle_3c_block(a, b, c):
+    return ints.int3c2e_sph(a.L, b.L, c.L, a.exps, a.coeffs, a.center, b.exps, b.coeffs, b.center,
+                            c.exps, c.coeffs, c.center)
+
+
+def test_three_center_tensor_full_and_packed(engine, small):
+    shells, _, aux, ob, ab = small
+    T = engine.int3c2e(ob, ab, layout="full").cpu().numpy()
+    Tp = engine.int3c2e(ob, ab, layout="packed").cpu().numpy()
+    offo = np.concatenate([[0], np.cumsum(_sizes(shells, True))])
+    offa = np.concatenate([[0], np.cumsum(_sizes(aux, True))])
+    gmax = np.abs(T).max()
+    rng = np.random.default_rng(1)
+    # (a) every shell triple of a random subset against the oracle.  Blocks that vanish by
+    # symmetry (same-centre shells) are compared on the absolute scale of the tensor.
+    for _ in range(300):
+        i, j, k = rng.integers(len(shells)), rng.integers(len(shells)), rng.integers(len(aux))
+        o = _oracle_3c_block(shells[i], shells[j], aux[k])
+        blk = T[offo[i]:offo[i + 1], offo[j]:offo[j + 1], offa[k]:offa[k + 1]].ravel()
+        ld = lambda s: (s.L, s.exps.astype(np.longdouble), s.coeffs.astype(np.longdouble), s.center.astype(np.longdouble))
+        tol = 1e-14 + 1e-12 * np.abs(o).max()
+        if np.abs(blk - o).max() > tol:
+            a, b, c = shells[i], shells[j], aux[k]
+            o80 = ints.int3c2e_sph(a.L, b.L, c.L, *ld(a)[1:], *ld(b)[1:], *ld(c)[1:])
+            noise = float(np.abs(o - o80).max())
+            assert float(np.abs(blk - o80).max()) <= 10 * noise + tol + 1e-15 * gmax, (i, j, k)
+    # (b) symmetry and packed == full
+    assert np.abs(T - T.transpose(1, 0, 2)).max() <= 1e-15 * gmax
+    row = 0
+    for i in range(len(shells)):
+        for j in range(i + 1):
+            ni, nj = offo[i + 1] - offo[i], offo[j + 1] - offo[j]
+            assert np.array_equal(Tp[row:row + ni * nj].reshape(ni, nj, -1), T[offo[i]:offo[i + 1], offo[j]:offo[j + 1]])
+            row += ni * nj
+    assert row == ob.packed_rows
+
+
+def test_three_center_aux_sharding_is_exact(engine, small):
+    """Sharding over contiguous aux-shell ranges (the multi-GPU partition) reproduces the
+    unsharded tensor bit for bit."""
+    _, _, aux, ob, ab = small
+    T = engine.int3c2e(ob, ab, layout="packed").cpu().numpy()
+    cuts = [0, 5, 6, 31, len(aux)]
+    parts = [engine.int3c2e(ob, ab, shell_range=(cuts[i], cuts[i + 1]), layout="packed").cpu().numpy()
+             for i in range(len(cuts) - 1)]
+    assert np.array_equal(np.concatenate(parts, axis=1), T)
+    h = engine.int3c2e_host(ob, ab, shell_range=(5, 31), layout="packed")
+    assert np.array_equal(h, np.concatenate(parts[1:3], axis=1))
+
+
+def test_translation_invariance_medium_system(engine):
+    """Size-independent property at a larger size: shifting every centre leaves ovlp/kin/2c2e/3c2e
+    unchanged (to rounding)."""
+    shells, sites = synthetic.orbital_basis(natoms=8, seed=11)
+    aux = synthetic.aux_basis(sites, seed=12)
+    shift = np.array([0.7, -1.3, 2.1])
+    from sympleints_b200.shells import Shell
+    mv = lambda ss: [Shell(s.L, s.center + shift, s.coeffs, s.exps, normalized=True) for s in ss]
+    b0, b1 = engine.basis(shells), engine.basis(mv(shells))
+    a0, a1 = engine.basis(aux), engine.basis(mv(aux))
+    for key in ("ovlp", "kin"):
+        m0, m1 = engine.int1e(key, b0).cpu().numpy(), engine.int1e(key, b1).cpu().numpy()
+        assert np.abs(m0 - m1).max() <= 1e-11 * np.abs(m0).max()
+    t0 = engine.int3c2e(b0, a0, layout="packed")
+    t1 = engine.int3c2e(b1, a1, layout="packed")
+    assert float((t0 - t1).abs().max()) <= 1e-10 * float(t0.abs().max())
+    m0, m1 = engine.int2c2e(a0).cpu().numpy(), engine.int2c2e(a1).cpu().numpy()
+    assert np.abs(m0 - m1).max() <= 1e-10 * np.abs(m0).max()
