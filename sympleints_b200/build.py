@@ -13,6 +13,8 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libsympleints_b200.so"
+GENDIR = CSRC / "generated"
+OBJDIR = PKG / "lib" / "obj"
 SOURCES = [CSRC / "si_lib.cu", CSRC / "si_program.cpp"]
 HEADERS = [CSRC / "si_machine.h", CSRC / "si_program.h", PKG.parent / "include" / "sympleints_b200.h"]
 NVCC_FLAGS = [
@@ -36,11 +38,46 @@ def needs_build():
     return any(p.stat().st_mtime > t for p in SOURCES + HEADERS)
 
 
-def build_library(force=False, verbose=False):
-    if not force and not needs_build():
+def generate_sources():
+    """Run the code generator (class-specialised 3c2e kernels) into csrc/generated/."""
+    from .codegen import gen3c2e
+
+    return [Path(f) for f in gen3c2e.write_sources(str(GENDIR))]
+
+
+def _compile_obj(src, obj, verbose):
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-c", "-o", str(obj), str(src)] + (["-Xptxas", "-v"] if verbose else [])
+    log = obj.with_suffix(".log")
+    with open(log, "w") as fh:
+        subprocess.check_call(cmd, stdout=fh, stderr=subprocess.STDOUT)
+    return obj
+
+
+def build_library(force=False, verbose=False, jobs=None):
+    gen = generate_sources()
+    deps = SOURCES + HEADERS + [CSRC / "si_g3.h", PKG / "codegen" / "gen3c2e.py"]
+    if not force and LIB.exists() and all(p.stat().st_mtime <= LIB.stat().st_mtime for p in deps):
         return LIB
     LIBDIR.mkdir(exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB)] + [str(s) for s in SOURCES]
+    OBJDIR.mkdir(exist_ok=True)
+    import concurrent.futures as cf
+    import os
+
+    todo = []
+    objs = []
+    hdr_time = max(p.stat().st_mtime for p in HEADERS + [CSRC / "si_g3.h"])
+    for src in gen + SOURCES:
+        obj = OBJDIR / (src.stem + ".o")
+        objs.append(obj)
+        if force or not obj.exists() or obj.stat().st_mtime < max(src.stat().st_mtime, hdr_time) or \
+                (src.name == "si_lib.cu" and obj.stat().st_mtime < (GENDIR / "g3_table.inc").stat().st_mtime):
+            todo.append((src, obj))
+    jobs = jobs or max(1, min(8, (os.cpu_count() or 2)))
+    with cf.ThreadPoolExecutor(jobs) as ex:
+        list(ex.map(lambda so: _compile_obj(so[0], so[1], verbose), todo))
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
+           "-o", str(LIB)] + [str(o) for o in objs]
     subprocess.check_call(cmd)
     return LIB
 

@@ -1,0 +1,754 @@
+"""Code generator: class-specialised CUDA kernels for the 3c2e_sph tensor (ab|c).
+
+This is the CUDA counterpart of the reference's generators (sympleints/main.py:206-323 for the
+sympy path, sympleints/graphs/generate.py + graphs/templates/int_3c2e_func.tpl for the graph
+path): for every class (La >= Lb, Lc) it emits straight-line device code for
+
+    Boys -> VRR(a, up to La+Lb) -> truncated aux VRR(c) -> contraction
+         -> C2S(c) -> HRR(b) + C2S(b) -> C2S(a) -> store
+
+(defs/coulomb.py:218-341; stage order of graphs/defs/int_3c2e.py:7-43).
+
+Execution model: EPT lanes of a warp co-operate on one shell tuple (32/EPT tuples per warp,
+EPT = 1 for the smallest classes = one thread per tuple, EPT = 32 for the largest = one warp per
+tuple).  Intermediates live in the tuple's shared-memory region; every shared-memory address is
+`immediate + per-lane register`, the per-lane registers (neighbour offsets a-1_i, factors a_i) are
+loaded once per kernel from small per-class tables.  All recurrence coefficients are per-tuple
+uniform registers.  The horizontal recurrence is evaluated per target a-component entirely in
+registers ("tile"), followed directly by C2S(b).
+"""
+from __future__ import annotations
+
+import math
+from fractions import Fraction
+
+
+# ----------------------------------------------------------------------------------------
+# small helpers (orderings identical to sympleints/helpers.py:42-49)
+# ----------------------------------------------------------------------------------------
+def ncart(l):
+    return (l + 1) * (l + 2) // 2
+
+
+def nsph(l):
+    return 2 * l + 1
+
+
+def cart_order(L):
+    out = []
+    for i in range(L + 1):
+        l = L - i
+        for n in range(i + 1):
+            out.append((l, i - n, n))
+    return out
+
+
+def cidx(a):
+    """Index of Cartesian component a within its shell."""
+    L = sum(a)
+    i = L - a[0]
+    return i * (i + 1) // 2 + a[2]
+
+
+def off(n):
+    """Flat offset of shell n when shells 0..n-1 are concatenated."""
+    return sum(ncart(j) for j in range(n))
+
+
+def fact2(n):
+    r = 1
+    while n > 1:
+        r *= n
+        n -= 2
+    return r
+
+
+def _c2s_complex(lx, ly, lz, m):
+    l = lx + ly + lz
+    am = abs(m)
+    j2 = lx + ly - am
+    if j2 < 0 or j2 % 2:
+        return 0.0
+    j = j2 // 2
+    lmm = l - am
+    sign = 1 if m >= 0 else -1
+    tot = 0
+    for i in range(lmm // 2 + 1):
+        if j > i:
+            continue
+        ifact = Fraction(math.comb(l, i) * math.comb(i, j) * (-1) ** i * math.factorial(2 * l - 2 * i),
+                         math.factorial(lmm - 2 * i))
+        ks = 0
+        for k in range(j + 1):
+            if lx - 2 * k < 0 or lx - 2 * k > am:
+                continue
+            e2 = sign * (am - lx + 2 * k)
+            ks += (1j ** (e2 % 4)) * math.comb(j, k) * math.comb(am, lx - 2 * k)
+        tot += complex(ks) * float(ifact)
+    rad = Fraction(math.factorial(2 * lx) * math.factorial(2 * ly) * math.factorial(2 * lz) * math.factorial(l)
+                   * math.factorial(lmm),
+                   math.factorial(2 * l) * math.factorial(lx) * math.factorial(ly) * math.factorial(lz)
+                   * math.factorial(l + am))
+    return tot * math.sqrt(float(rad)) / (2**l * math.factorial(l))
+
+
+_C2S_CACHE = {}
+
+
+def cart2sph(l):
+    """Real C2S matrix rows m=-l..l (sympleints/cart2sph.py:163-202), list of lists."""
+    if l in _C2S_CACHE:
+        return _C2S_CACHE[l]
+    comps = cart_order(l)
+    M = [[0.0] * len(comps) for _ in range(2 * l + 1)]
+    for ci, (lx, ly, lz) in enumerate(comps):
+        for mi, m in enumerate(range(-l, l + 1)):
+            c = _c2s_complex(lx, ly, lz, m)
+            if m != 0:
+                cm = _c2s_complex(lx, ly, lz, -m)
+                if m < 0:
+                    c = (c + cm) / math.sqrt(2)
+                else:
+                    c = (c - cm) / (1j * math.sqrt(2))
+            v = complex(c).real
+            assert abs(complex(c).imag) < 1e-13
+            M[mi][ci] = 0.0 if abs(v) <= 1e-14 else v
+    _C2S_CACHE[l] = M
+    return M
+
+
+def lmn_factors(l):
+    return [1.0 / math.sqrt(fact2(2 * a - 1) * fact2(2 * b - 1) * fact2(2 * c - 1)) for (a, b, c) in cart_order(l)]
+
+
+def lit(x):
+    """C++ double literal with full precision."""
+    s = repr(float(x))
+    if "e" not in s and "." not in s and "inf" not in s:
+        s += ".0"
+    return s
+
+
+def pow2ceil(n):
+    p = 1
+    while p < n:
+        p *= 2
+    return p
+
+
+# ----------------------------------------------------------------------------------------
+class ClassGen:
+    """Emit the device function + kernel for one class."""
+
+    def __init__(self, La, Lb, Lc, ept=None):
+        assert La >= Lb
+        self.La, self.Lb, self.Lc = La, Lb, Lc
+        self.L = L = La + Lb
+        self.NA = off(L + 1)                 # flat a size, shells 0..L
+        self.n_ap = self.NA - off(La)        # target a' (shells La..L)
+        self.ncc = ncart(Lc)
+        self.nm = nsph(Lc)
+        self.nca, self.ncb = ncart(La), ncart(Lb)
+        self.nsa, self.nsb = nsph(La), nsph(Lb)
+        if ept is None:
+            ept = min(32, pow2ceil(max(1, (self.n_ap + 1) // 2)))
+        self.EPT = ept
+        self.TPW = 32 // ept
+        self.name = f"{La}{Lb}{Lc}"
+        self.lines = []
+        self.ind = 1
+        self._layout()
+
+    # ---- shared-memory layout (doubles, per tuple) ------------------------------------
+    def amin(self, level):
+        return max(0, self.La - (self.Lc - level))
+
+    def _layout(self):
+        L, Lc = self.L, self.Lc
+        o = 0
+        self.S_OFF = o          # scalars: PA[3], CPC[3], BPOW[L+1]
+        self.S_PA, self.S_CPC, self.S_BPOW = 0, 3, 6
+        o += 6 + (L + 1)
+        if o % 2:
+            o += 1
+        # X[c][a'] persistent over primitives
+        self.X_OFF = o
+        o += self.ncc * self.n_ap
+        x_end = o
+        # primitive temporaries
+        self.V_OFF = {}
+        for n in range(L + 1):
+            for jn in range(L - n + 1):
+                self.V_OFF[(n, jn)] = o
+                o += ncart(n)
+        # D-tree arrays per level 0..Lc-1 (non-leaf), flat index relative to off(amin(level))
+        self.D_OFF = {}
+        for lev in range(0, max(Lc, 1)):
+            self.D_OFF[lev] = o - off(self.amin(lev))   # address of flat index f is D_OFF[lev] + f
+            o += self.NA - off(self.amin(lev))
+        prim_end = o
+        # contracted phase: Y[m][a'] over the primitive temporaries, Z over X (or after Y)
+        self.Y_OFF = x_end
+        y_end = x_end + self.nm * self.n_ap
+        zsize = self.nm * self.nca * self.nsb
+        if self.Lb == 0:
+            self.Z_OFF = self.Y_OFF     # Z == Y (n_ap == nca, nsb == 1)
+            z_end = y_end
+        elif zsize <= x_end - self.X_OFF:
+            self.Z_OFF = self.X_OFF
+            z_end = y_end
+        else:
+            self.Z_OFF = y_end
+            z_end = y_end + zsize
+        w = max(prim_end, y_end, z_end)
+        if w % 2 == 0:
+            w += 1               # odd stride: conflict-free when several tuples share a warp
+        self.WSZ = w
+
+    # ---- emission helpers ---------------------------------------------------------------
+    def emit(self, s=""):
+        self.lines.append("    " * self.ind + s)
+
+    def open(self, s):
+        self.emit(s + " {")
+        self.ind += 1
+
+    def close(self, s="}"):
+        self.ind -= 1
+        self.emit(s)
+
+    def nslots(self, count):
+        return (count + self.EPT - 1) // self.EPT
+
+    # ---- per-class metadata tables ----------------------------------------------------
+    def vrr_meta(self):
+        """Per shell n >= 1, per component k: direction d, index k1 in shell n-1, k2 in shell n-2, fac."""
+        tab = {}
+        for n in range(1, self.L + 1):
+            row = []
+            for a in cart_order(n):
+                d = next(i for i in range(3) if a[i] > 0)
+                am = list(a)
+                am[d] -= 1
+                k1 = cidx(am)
+                fac = a[d] - 1
+                if fac > 0:
+                    amm = list(am)
+                    amm[d] -= 1
+                    k2 = cidx(amm)
+                else:
+                    k2 = 0
+                row.append((d, k1, k2, fac))
+            tab[n] = row
+        return tab
+
+    def dtree_meta(self):
+        """Per flat index f (shells 0..L): for d in x,y,z: delta to flat index of a-1_d (0 if a_d == 0), a_d."""
+        out = []
+        for n in range(self.L + 1):
+            for a in cart_order(n):
+                f = off(n) + cidx(a)
+                ent = []
+                for d in range(3):
+                    if a[d] > 0:
+                        am = list(a)
+                        am[d] -= 1
+                        fm = off(n - 1) + cidx(am)
+                        ent.append((fm - f, a[d]))
+                    else:
+                        ent.append((0, 0))
+                out.append((n, ent))
+        return out
+
+    # ---- the generator ----------------------------------------------------------------------
+    def generate(self):
+        La, Lb, Lc, L = self.La, self.Lb, self.Lc, self.L
+        EPT, TPW = self.EPT, self.TPW
+        name = self.name
+        E = self.emit
+        self.lines = []
+        self.ind = 0
+        vm = self.vrr_meta()
+        dm = self.dtree_meta()
+        # ---- tables
+        # VRR: packed int per (n,k): d | fac<<2 | k1<<8 | k2<<16
+        for n in range(1, L + 1):
+            vals = [d | (fac << 2) | (k1 << 8) | (k2 << 16) for (d, k1, k2, fac) in vm[n]]
+            E(f"__device__ const int g3_vrr_{name}_{n}[{len(vals)}] = {{{', '.join(map(str, vals))}}};")
+        if Lc > 0:
+            # D-tree: per flat index: byte... element deltas (<=0) packed 3x10 bits (as positive magnitudes), shell, factors 3x4 bits
+            vals = []
+            for (n, ent) in dm:
+                v = 0
+                for d in range(3):
+                    v |= ((-ent[d][0]) & 0xFF) << (8 * d)
+                v |= (n & 0xF) << 24
+                vals.append(v)
+            E(f"__device__ const int g3_dd_{name}[{len(vals)}] = {{{', '.join(map(str, vals))}}};")
+            vals = []
+            for (n, ent) in dm:
+                v = 0
+                for d in range(3):
+                    v |= (ent[d][1] & 0xF) << (4 * d)
+                vals.append(v)
+            E(f"__device__ const int g3_df_{name}[{len(vals)}] = {{{', '.join(map(str, vals))}}};")
+        E("")
+        E(f"// class ({La}{Lb}|{Lc}): EPT={EPT} lanes per tuple, {TPW} tuples per warp, {self.WSZ} doubles of shared memory per tuple")
+        E(f"SI_G3_DEV void g3_body_{name}(const G3Args& A, const int lane, double* wbase) {{")
+        self.ind = 1
+        E(f"constexpr int EPT = {EPT}, TPW = {TPW}, WSZ = {self.WSZ};")
+        E("const int q = lane % EPT, tl = lane / EPT;")
+        E("double* const W = wbase + tl * WSZ;")
+        E("(void)q;")
+        # ---- per-lane metadata
+        nsl_v = {n: self.nslots(ncart(n)) for n in range(1, L + 1)}
+        for n in range(1, L + 1):
+            for s in range(nsl_v[n]):
+                E(f"int vm_{n}_{s}; {{ int k = q + EPT * {s}; vm_{n}_{s} = g3_vrr_{name}_{n}[k < {ncart(n)} ? k : 0]; }}")
+        nsl_d = self.nslots(self.NA)
+        if Lc > 0:
+            for s in range(nsl_d):
+                E(f"int dd_{s}, ds_{s}; double dfx_{s}, dfy_{s}, dfz_{s}; {{ int f = q + EPT * {s}; if (f >= {self.NA}) f = {self.NA - 1}; "
+                  f"int v = g3_dd_{name}[f]; int w = g3_df_{name}[f]; dd_{s} = v; ds_{s} = (v >> 24) & 0xF; "
+                  f"dfx_{s} = (double)(w & 0xF); dfy_{s} = (double)((w >> 4) & 0xF); dfz_{s} = (double)((w >> 8) & 0xF); }}")
+        E("")
+        # ---- work loop over tuple groups
+        self.open("for (;;)")
+        E("long long grp = si_g3_next_group(A.counter, lane);")
+        E("if (grp >= A.ngroups) break;")
+        E("// group -> (pair, first aux of the group); tuples beyond the run end recompute the last valid one")
+        E("const int ip = (int)(grp / A.groups_per_pair);")
+        E("const int gi = (int)(grp - (long long)ip * A.groups_per_pair);")
+        E("int ic = gi * TPW + tl;")
+        E("const bool valid = ic < A.naux_c;")
+        E("if (!valid) ic = A.naux_c - 1;")
+        E("const SiPairItem it = A.pairs[ip];")
+        E("const int sc = A.auxlist[ic];")
+        E("const int Ka = A.orb.nprim[it.sa], Kb = A.orb.nprim[it.sb], Kc = A.aux.nprim[sc];")
+        E("const int pa0 = A.orb.poff[it.sa], pb0 = A.orb.poff[it.sb], pc0 = A.aux.poff[sc];")
+        E("double Ax[3], Bx[3], Cx[3], AB[3];")
+        self.open("for (int d = 0; d < 3; ++d)")
+        E("Ax[d] = A.orb.cen[3 * it.sa + d]; Bx[d] = A.orb.cen[3 * it.sb + d]; Cx[d] = A.aux.cen[3 * sc + d]; AB[d] = Ax[d] - Bx[d];")
+        self.close()
+        E("const int Kc_max = si_g3_warp_max(Kc);")
+        E("bool first = true;")
+        self.open("for (int ia = 0; ia < Ka; ++ia)")
+        E("const double ax = A.orb.exps[pa0 + ia], da = A.orb.coef[pa0 + ia];")
+        self.open("for (int ib = 0; ib < Kb; ++ib)")
+        E("const double bx = A.orb.exps[pb0 + ib], db = A.orb.coef[pb0 + ib];")
+        E("const double p = ax + bx, oop = 1.0 / p, mu = ax * bx * oop;")
+        E("double P[3], PA[3]; double r2ab = 0.0;")
+        self.open("for (int d = 0; d < 3; ++d)")
+        E("P[d] = (ax * Ax[d] + bx * Bx[d]) * oop; PA[d] = P[d] - Ax[d]; r2ab += AB[d] * AB[d];")
+        self.close()
+        E("const double Kab = exp(-mu * r2ab) * da * db;")
+        self.open("for (int ik = 0; ik < Kc_max; ++ik)")
+        E("// tuples with fewer aux primitives repeat their last one with zero weight")
+        E("const int ikk = ik < Kc ? ik : Kc - 1;")
+        E("const double cx = A.aux.exps[pc0 + ikk], dc = ik < Kc ? A.aux.coef[pc0 + ikk] : 0.0;")
+        self._emit_primitive()
+        E("first = false;")
+        self.close()  # ik
+        self.close()  # ib
+        self.close()  # ia
+        E("si_g3_syncwarp();")
+        self._emit_c2s_c()
+        E("si_g3_syncwarp();")
+        if Lb > 0:
+            self._emit_hrr_c2sb()
+            E("si_g3_syncwarp();")
+        self._emit_c2s_a_store()
+        E("si_g3_syncwarp();")
+        self.close()  # for(;;)
+        self.close()  # function
+        E("")
+        # kernel wrapper
+        E(f"SI_G3_GLOBAL void g3_kernel_{name}(G3Args A) {{")
+        E("    SI_G3_KERNEL_PROLOGUE")
+        E(f"    g3_body_{name}(A, g3_lane, g3_smem + (size_t)g3_warp * {self.WSZ * TPW});")
+        E("}")
+        E("")
+        return "\n".join(self.lines)
+
+    # ---- primitive phase ----------------------------------------------------------------
+    def _emit_primitive(self):
+        La, Lb, Lc, L = self.La, self.Lb, self.Lc, self.L
+        EPT = self.EPT
+        E = self.emit
+        vm_n = self.vrr_meta()
+        E("const double pc_ = p + cx;")
+        E("const double rho = p * cx / pc_;")
+        E("const double rho_p = rho * oop;")
+        E("double PC[3]; double r2pc = 0.0;")
+        self.open("for (int d = 0; d < 3; ++d)")
+        E("PC[d] = P[d] - Cx[d]; r2pc += PC[d] * PC[d];")
+        self.close()
+        E("const double T = rho * r2pc;")
+        E("const double pref = 2.0 * SI_PI_25 / (sqrt(pc_) * p * cx) * Kab * dc;")
+        E("const double oo2p = 0.5 * oop, c2 = -0.5 * oop * rho_p;")
+        E("const double beta = 0.5 / pc_;      // (rho/c)/(2p)")
+        E("const double binv = 2.0 * pc_;")
+        E("const double rho_c = rho / cx;")
+        E("const double alx = rho_c * PC[0], aly = rho_c * PC[1], alz = rho_c * PC[2];")
+        E("(void)alx; (void)aly; (void)alz; (void)beta; (void)binv;")
+        E("si_g3_syncwarp();   // previous primitive's readers are done")
+        # scalars to shared memory (lane q==0 of the tuple)
+        self.open("if (q == 0)")
+        for d in range(3):
+            E(f"W[{self.S_PA + d}] = PA[{d}]; W[{self.S_CPC + d}] = -rho_p * PC[{d}];")
+        if Lc > 0:
+            E("{ double bp = 1.0;")
+            for n in range(L + 1):
+                E(f"  W[{self.S_BPOW + n}] = bp; bp *= beta;")
+            E("}")
+        self.close()
+        # Boys base values: V(0, jn, 0) = pref * F_{Lc+jn}(T)
+        nb = L + 1
+        self.open(f"for (int j = q; j < {nb}; j += EPT)")
+        E(f"W[{self.V_OFF[(0, 0)]} + j] = pref * si_boys(A.boys, {Lc} + j, T);")
+        self.close()
+        # note: V(0,jn,0) are contiguous since ncart(0)=1
+        for jn in range(nb):
+            assert self.V_OFF[(0, jn)] == self.V_OFF[(0, 0)] + jn
+        E("si_g3_syncwarp();")
+        # ---- VRR shells
+        for n in range(1, L + 1):
+            nc = ncart(n)
+            njn = L - n + 1
+            for s in range(self.nslots(nc)):
+                partial = (s + 1) * EPT > nc
+                if partial:
+                    self.open(f"if (q + EPT * {s} < {nc})")
+                else:
+                    self.open("")
+                E(f"const int m_ = vm_{n}_{s}; const int d_ = m_ & 3; const int k1 = (m_ >> 8) & 0xFF; const int k2 = (m_ >> 16) & 0xFF;")
+                E(f"const double pa_ = W[{self.S_PA} + d_], cp_ = W[{self.S_CPC} + d_];")
+                if n >= 2:
+                    E("const double fc_ = (double)((m_ >> 2) & 0xF); const double f1 = fc_ * oo2p, f2 = fc_ * c2;")
+                E(f"const int k_ = q + EPT * {s};")
+                E(f"double u0 = W[{self.V_OFF[(n - 1, 0)]} + k1], u1;")
+                if n >= 2:
+                    E(f"double w0 = W[{self.V_OFF[(n - 2, 0)]} + k2], w1;")
+                for jn in range(njn):
+                    E(f"u1 = W[{self.V_OFF[(n - 1, jn + 1)]} + k1];")
+                    if n >= 2:
+                        E(f"w1 = W[{self.V_OFF[(n - 2, jn + 1)]} + k2];")
+                        E(f"W[{self.V_OFF[(n, jn)]} + k_] = fma(f2, w1, fma(f1, w0, fma(pa_, u0, cp_ * u1)));")
+                        E("w0 = w1;")
+                    else:
+                        E(f"W[{self.V_OFF[(n, jn)]} + k_] = fma(pa_, u0, cp_ * u1);")
+                    E("u0 = u1;")
+                self.close()
+            E("si_g3_syncwarp();")
+        # ---- D-tree
+        if Lc == 0:
+            # X[0][a'] (+)= V(n,0,k) for shells La..L
+            for n in range(La, L + 1):
+                nc = ncart(n)
+                for s in range(self.nslots(nc)):
+                    partial = (s + 1) * EPT > nc
+                    self.open(f"if (q + EPT * {s} < {nc})" if partial else "")
+                    xa = self.X_OFF + off(n) - off(La)
+                    E(f"const int k_ = q + EPT * {s}; const double v_ = W[{self.V_OFF[(n, 0)]} + k_];")
+                    E(f"if (first) W[{xa} + k_] = v_; else W[{xa} + k_] += v_;")
+                    self.close()
+            return
+        # root: h[f] = V(n, 0, k) * binv^n for shells amin(0)..L, stored at D_OFF[0] + f
+        E("{ double bq = 1.0;")
+        self.ind += 1
+        for n in range(0, L + 1):
+            if n >= self.amin(0):
+                nc = ncart(n)
+                for s in range(self.nslots(nc)):
+                    partial = (s + 1) * EPT > nc
+                    cond = f"if (q + EPT * {s} < {nc}) " if partial else ""
+                    E(f"{cond}W[{self.D_OFF[0] + off(n)} + q + EPT * {s}] = W[{self.V_OFF[(n, 0)]} + q + EPT * {s}] * bq;")
+            E("bq *= binv;")
+        self.ind -= 1
+        E("}")
+        E("si_g3_syncwarp();")
+        # DFS over monomials; direction sequences non-decreasing (x.., y.., z..)
+        nsl = self.nslots(self.NA)
+        # per-slot: own root values + beta powers for the leaves
+        for s in range(nsl):
+            lo = off(self.amin(0))
+            E(f"double r0_{s} = 0.0; {{ const int f = q + EPT * {s}; if (f >= {lo} && f < {self.NA}) r0_{s} = W[{self.D_OFF[0]} + f]; }}")
+        for s in range(nsl):
+            E(f"const double bp_{s} = W[{self.S_BPOW} + ds_{s}];")
+        al = ["alx", "aly", "alz"]
+        dfn = ["dfx", "dfy", "dfz"]
+        ccomps = cart_order(Lc)
+
+        def rec(c, level, lastd):
+            # values of node c are in registers r{level}_{s}; its array is at D_OFF[level]
+            for d in range(lastd, 3):
+                c2 = list(c)
+                c2[d] += 1
+                lev2 = level + 1
+                leaf = lev2 == Lc
+                lo2 = off(self.amin(lev2))
+                self.open("")
+                E(f"// node {tuple(c2)} <- {tuple(c)} (+1_{'xyz'[d]})")
+                for s in range(nsl):
+                    smin, smax = s * EPT, s * EPT + EPT - 1
+                    if smax < lo2 or smin >= self.NA:
+                        if not leaf:
+                            E(f"double r{lev2}_{s} = 0.0;")
+                        continue
+                    full = smin >= lo2 and smax < self.NA
+                    E("{" if leaf else f"double r{lev2}_{s} = 0.0; {{")
+                    self.ind += 1
+                    E(f"const int f = q + EPT * {s};")
+                    if not full:
+                        self.open(f"if (f >= {lo2} && f < {self.NA})")
+                    E(f"const double nb_ = W[{self.D_OFF[level]} + f - ((dd_{s} >> {8 * d}) & 0xFF)];")
+                    E(f"const double v_ = fma({dfn[d]}_{s}, nb_, {al[d]} * r{level}_{s});")
+                    if leaf:
+                        ci = cidx(c2)
+                        xa = self.X_OFF + ci * self.n_ap - off(La)
+                        E(f"if (first) W[{xa} + f] = bp_{s} * v_; else W[{xa} + f] = fma(bp_{s}, v_, W[{xa} + f]);")
+                    else:
+                        E(f"r{lev2}_{s} = v_; W[{self.D_OFF[lev2]} + f] = v_;")
+                    if not full:
+                        self.close()
+                    self.ind -= 1
+                    E("}")
+                if not leaf:
+                    E("si_g3_syncwarp();")
+                    rec(c2, lev2, d)
+                    E("si_g3_syncwarp();   // children done before the array is overwritten")
+                self.close()
+
+        self.open("")
+        rec([0, 0, 0], 0, 0)
+        self.close()
+
+    # ---- C2S on c: Y[m][a'] = sum_c M[m][c] X[c][a'] -------------------------------------
+    def _emit_c2s_c(self):
+        E = self.emit
+        EPT = self.EPT
+        Lc = self.Lc
+        M = cart2sph(Lc)
+        f = lmn_factors(Lc)
+        n_ap = self.n_ap
+        for s in range(self.nslots(n_ap)):
+            partial = (s + 1) * EPT > n_ap
+            self.open(f"if (q + EPT * {s} < {n_ap})" if partial else "")
+            E(f"const int f_ = q + EPT * {s};")
+            for c in range(self.ncc):
+                E(f"const double x{c} = W[{self.X_OFF + c * n_ap} + f_];")
+            for m in range(self.nm):
+                terms = [(M[m][c] * f[c], c) for c in range(self.ncc) if M[m][c] != 0.0]
+                expr = None
+                for (coef, c) in terms:
+                    expr = f"{lit(coef)} * x{c}" if expr is None else f"fma({lit(coef)}, x{c}, {expr})"
+                E(f"const double y{m} = {expr};")
+            # stores after all loads (Y may not alias X: different regions)
+            for m in range(self.nm):
+                E(f"W[{self.Y_OFF + m * n_ap} + f_] = y{m};")
+            self.close()
+
+    # ---- HRR tile per (target a, m) + C2S(b): Z[m][a][jb] ---------------------------------
+    def _emit_hrr_c2sb(self):
+        E = self.emit
+        La, Lb, EPT = self.La, self.Lb, self.EPT
+        nca, nm, nsb, n_ap = self.nca, self.nm, self.nsb, self.n_ap
+        nit = nca * nm
+        Mb = cart2sph(Lb)
+        fb = lmn_factors(Lb)
+        # symbolic tile: nodes (k, b) = (a + k, b); b built by first-nonzero direction
+        memo = {}
+        order = []
+
+        def node(k, b):
+            key = (tuple(k), tuple(b))
+            if key in memo:
+                return memo[key]
+            if sum(b) == 0:
+                name = "i" + "_".join(map(str, k))
+                memo[key] = name
+                order.append(("in", key, name))
+                return name
+            d = next(i for i in range(3) if b[i] > 0)
+            bm = list(b)
+            bm[d] -= 1
+            kp = list(k)
+            kp[d] += 1
+            n1 = node(kp, bm)
+            n2 = node(k, bm)
+            name = "t" + "_".join(map(str, k)) + "__" + "_".join(map(str, b))
+            memo[key] = name
+            order.append(("op", key, name, n1, n2, d))
+            return name
+
+        targets = [node([0, 0, 0], list(b)) for b in cart_order(Lb)]
+        self.open(f"for (int item = q; item < {nit}; item += EPT)")
+        E(f"const int ai = item / {nm}, m = item - ai * {nm};")
+        E("int ia_ = 0; while ((ia_ + 1) * (ia_ + 2) / 2 <= ai) ++ia_;   // row of the target a (l = La - ia_)")
+        E(f"const int yb = {self.Y_OFF} + m * {n_ap} + ai;")
+        for ik in range(Lb + 1):
+            E(f"const int yb{ik} = yb + ia_ * {ik};")
+        # inputs: idx(a+k) - idx-base: off(La+|k|)-off(La) + row(ik) + nz_k + ia*ik   (+ ai)
+        for ent in order:
+            if ent[0] == "in":
+                k = ent[1][0]
+                ik = k[1] + k[2]
+                nk = sum(k)
+                const = off(La + nk) - off(La) + ik * (ik + 1) // 2 + k[2]
+                E(f"const double {ent[2]} = W[yb{ik} + {const}];")
+            else:
+                _, key, name, n1, n2, d = ent
+                E(f"const double {name} = fma(AB[{d}], {n2}, {n1});")
+        # C2S(b)
+        for jb in range(nsb):
+            expr = None
+            for j in range(self.ncb):
+                coef = Mb[jb][j] * fb[j]
+                if Mb[jb][j] == 0.0:
+                    continue
+                expr = f"{lit(coef)} * {targets[j]}" if expr is None else f"fma({lit(coef)}, {targets[j]}, {expr})"
+            E(f"W[{self.Z_OFF} + (m * {nca} + ai) * {nsb} + {jb}] = {expr};")
+        self.close()
+
+    # ---- C2S(a) + global store --------------------------------------------------------------
+    def _emit_c2s_a_store(self):
+        E = self.emit
+        La, EPT = self.La, self.EPT
+        nca, nm, nsb, nsa = self.nca, self.nm, self.nsb, self.nsa
+        Ma = cart2sph(La)
+        fa = lmn_factors(La)
+        nit = nsb * nm
+        E("const long long col = (long long)(A.aux.foff[sc] - A.col_begin);")
+        E("const int fa0 = A.orb.foff ? A.orb.foff[it.sa] : 0, fb0 = A.orb.foff ? A.orb.foff[it.sb] : 0;")
+        self.open(f"for (int item = q; item < {nit}; item += EPT)")
+        E(f"const int jb = item / {nm}, m = item - jb * {nm};")
+        for a in range(nca):
+            E(f"const double z{a} = W[{self.Z_OFF} + (m * {nca} + {a}) * {nsb} + jb];")
+        for ia in range(nsa):
+            expr = None
+            for a in range(nca):
+                if Ma[ia][a] == 0.0:
+                    continue
+                coef = Ma[ia][a] * fa[a]
+                expr = f"{lit(coef)} * z{a}" if expr is None else f"fma({lit(coef)}, z{a}, {expr})"
+            E(f"const double o{ia} = {expr};")
+        self.open("if (valid)")
+        for ia in range(nsa):
+            E(f"si_g3_store(A.od, it, fa0, fb0, {nsa}, {nsb}, {nm}, col, {ia}, jb, m, o{ia});")
+        self.close()
+        self.close()
+
+
+HEADER = """// GENERATED by sympleints_b200/codegen/gen3c2e.py -- DO NOT EDIT.
+#include "../si_g3.h"
+"""
+
+
+def generate_file(classes):
+    parts = [HEADER]
+    for (La, Lb, Lc) in classes:
+        parts.append(ClassGen(La, Lb, Lc).generate())
+    return "\n".join(parts)
+
+
+def all_classes(lmax=4, lauxmax=5):
+    return [(a, b, c) for a in range(lmax + 1) for b in range(a + 1) for c in range(lauxmax + 1)]
+
+
+def class_info(lmax=4, lauxmax=5):
+    return {(a, b, c): ClassGen(a, b, c) for (a, b, c) in all_classes(lmax, lauxmax)}
+
+
+# ----------------------------------------------------------------------------------------
+# file emission: several translation units (parallel nvcc) + a class table + launcher
+# ----------------------------------------------------------------------------------------
+def write_sources(outdir, lmax=4, lauxmax=5, nparts=15):
+    """Write generated/g3_part_XX.cu, generated/g3_table.inc.  Returns the list of .cu files."""
+    import os
+
+    os.makedirs(outdir, exist_ok=True)
+    classes = all_classes(lmax, lauxmax)
+    gens = {c: ClassGen(*c) for c in classes}
+    # balance parts by generated size (roughly WSZ-proportional): group by (La, Lb)
+    pairs = sorted({(a, b) for (a, b, _) in classes})
+    parts = [[] for _ in range(nparts)]
+    load = [0] * nparts
+    for pr in sorted(pairs, key=lambda p: -(off(p[0] + p[1] + 1))):
+        i = load.index(min(load))
+        cl = [c for c in classes if (c[0], c[1]) == pr]
+        parts[i].extend(cl)
+        load[i] += sum(gens[c].WSZ for c in cl)
+    files = []
+    table = []
+    for pi, cl in enumerate(parts):
+        if not cl:
+            continue
+        src = [HEADER]
+        for c in cl:
+            src.append(gens[c].generate())
+        # launcher for this part
+        src.append("#if !defined(SI_G3_HOST_EMU)")
+        src.append(f"int g3_launch_part_{pi}(int id, const G3Args& A, int grid, int block, size_t smem, cudaStream_t s) {{")
+        src.append("    switch (id) {")
+        for c in cl:
+            g = gens[c]
+            cid = c[0] * 100 + c[1] * 10 + c[2]
+            src.append(f"        case {cid}: cudaFuncSetAttribute(g3_kernel_{g.name}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);"
+                       f" g3_kernel_{g.name}<<<grid, block, smem, s>>>(A); return 0;")
+            table.append((cid, pi, g.EPT, g.TPW, g.WSZ))
+        src.append("        default: return 1;")
+        src.append("    }")
+        src.append("}")
+        src.append("#endif")
+        fn = os.path.join(outdir, f"g3_part_{pi:02d}.cu")
+        text = "\n".join(src) + "\n"
+        if not os.path.exists(fn) or open(fn).read() != text:
+            open(fn, "w").write(text)
+        files.append(fn)
+    # table include
+    lines = ["// GENERATED -- class table of the specialised 3c2e kernels: {id, part, EPT, TPW, WSZ}"]
+    lines.append("static const int g3_table[][5] = {")
+    for t in sorted(table):
+        lines.append("    {%d, %d, %d, %d, %d}," % t)
+    lines.append("};")
+    for pi, cl in enumerate(parts):
+        if cl:
+            lines.append(f"int g3_launch_part_{pi}(int id, const G3Args& A, int grid, int block, size_t smem, cudaStream_t s);")
+    lines.append("static int g3_launch(int part, int id, const G3Args& A, int grid, int block, size_t smem, cudaStream_t s) {")
+    lines.append("    switch (part) {")
+    for pi, cl in enumerate(parts):
+        if cl:
+            lines.append(f"        case {pi}: return g3_launch_part_{pi}(id, A, grid, block, smem, s);")
+    lines.append("        default: return 1;")
+    lines.append("    }")
+    lines.append("}")
+    fn = os.path.join(outdir, "g3_table.inc")
+    text = "\n".join(lines) + "\n"
+    if not os.path.exists(fn) or open(fn).read() != text:
+        open(fn, "w").write(text)
+    return files
+
+
+def write_emu_source(path, classes):
+    """TEST-ONLY: one translation unit with the bodies of `classes` and a switch, for tests/emu."""
+    src = ["#define SI_G3_HOST_EMU 1", HEADER.replace("../si_g3.h", "../../sympleints_b200/csrc/si_g3.h")]
+    for c in classes:
+        src.append(ClassGen(*c).generate())
+    src.append("struct G3EmuClass { int id, ept, tpw, wsz; void (*body)(const G3Args&, int, double*); };")
+    src.append("static const G3EmuClass g3_emu_classes[] = {")
+    for c in classes:
+        g = ClassGen(*c)
+        src.append(f"    {{{c[0] * 100 + c[1] * 10 + c[2]}, {g.EPT}, {g.TPW}, {g.WSZ}, g3_body_{g.name}}},")
+    src.append("};")
+    src.append(f"static const int g3_emu_nclasses = {len(classes)};")
+    text = "\n".join(src) + "\n"
+    import os
+    if not os.path.exists(path) or open(path).read() != text:
+        open(path, "w").write(text)
+
+
+if __name__ == "__main__":
+    import sys
+    out = sys.argv[1] if len(sys.argv) > 1 else "sympleints_b200/csrc/generated"
+    for f in write_sources(out):
+        print(f)

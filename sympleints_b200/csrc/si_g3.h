@@ -1,0 +1,115 @@
+// Support header for the GENERATED 3c2e kernels (codegen/gen3c2e.py).
+//
+// The same generated source compiles two ways:
+//   * nvcc (default): real kernels, __syncwarp / __shfl_sync / atomicAdd;
+//   * -DSI_G3_HOST_EMU with g++: TEST-ONLY warp emulation -- 32 host threads per warp, a
+//     std::barrier for __syncwarp -- used by tests/emu to check the generated code without a GPU.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "si_machine.h"
+
+struct BasisDev {
+    const int* L;
+    const int* nprim;
+    const int* poff;
+    const int* foff;  // function offsets (sph or cart, chosen by the host)
+    const double* cen;
+    const double* exps;
+    const double* coef;
+};
+
+struct SiPairItem {
+    int sa, sb;       // shell indices; L(sa) >= L(sb)
+    int swapped;      // packed layout: 1 if sa is the column shell of the (i>=j) block
+    int pad;
+    long long prow;   // first row of the pair block in the packed 3-index layout
+};
+
+enum StoreMode { STORE_BLOCK = 0, STORE_MATRIX = 1, STORE_3C_FULL = 2, STORE_3C_PACKED = 3 };
+
+struct OutDesc {
+    double* out;
+    long long ld;           // matrix: nbf ; 3c: naux_local
+    long long comp_stride;  // matrix: nbf*nbf
+    long long nbf;
+    int mode;
+};
+
+struct G3Args {
+    BasisDev orb, aux;
+    const SiPairItem* pairs;
+    int npairs;
+    const int* auxlist;   // aux shells of this class (same Lc)
+    int naux_c;
+    int col_begin;
+    int groups_per_pair;  // ceil(naux_c / tuples-per-warp)
+    long long ngroups;    // npairs * groups_per_pair
+    OutDesc od;
+    int* counter;
+    SiBoys boys;
+};
+
+#if defined(SI_G3_HOST_EMU)
+// ------------------------------------------------------------------ host warp emulation
+#include <atomic>
+#include <barrier>
+struct SiG3EmuWarp {
+    std::barrier<>* bar;
+    volatile long long xchg[32];
+};
+extern thread_local SiG3EmuWarp* si_g3_emu_warp;
+extern thread_local int si_g3_emu_lane;
+#define __device__
+#define SI_G3_DEV static inline
+#define SI_G3_GLOBAL static inline
+#define SI_G3_KERNEL_PROLOGUE                                   \
+    extern thread_local double* si_g3_emu_smem;                 \
+    double* g3_smem = si_g3_emu_smem;                           \
+    const int g3_lane = si_g3_emu_lane, g3_warp = 0;
+static inline void si_g3_syncwarp() { si_g3_emu_warp->bar->arrive_and_wait(); }
+static inline long long si_g3_next_group(int* counter, int lane) {
+    if (lane == 0) si_g3_emu_warp->xchg[0] = __atomic_fetch_add(counter, 1, __ATOMIC_SEQ_CST);
+    si_g3_syncwarp();
+    long long v = si_g3_emu_warp->xchg[0];
+    si_g3_syncwarp();
+    return v;
+}
+static inline int si_g3_warp_max(int v) {
+    si_g3_emu_warp->xchg[si_g3_emu_lane] = v;
+    si_g3_syncwarp();
+    int m = v;
+    for (int i = 0; i < 32; ++i) m = (int)si_g3_emu_warp->xchg[i] > m ? (int)si_g3_emu_warp->xchg[i] : m;
+    si_g3_syncwarp();
+    return m;
+}
+#else
+// ------------------------------------------------------------------ device
+#define SI_G3_DEV __device__ __forceinline__
+#define SI_G3_GLOBAL __global__ __launch_bounds__(128)
+#define SI_G3_KERNEL_PROLOGUE              \
+    extern __shared__ double g3_smem[];    \
+    const int g3_lane = threadIdx.x & 31, g3_warp = threadIdx.x >> 5;
+__device__ __forceinline__ void si_g3_syncwarp() { __syncwarp(); }
+__device__ __forceinline__ long long si_g3_next_group(int* counter, int lane) {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(counter, 1);
+    return (long long)__shfl_sync(0xffffffffu, v, 0);
+}
+__device__ __forceinline__ int si_g3_warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+#endif
+
+// element (ia, jb, m) of the (a_sph, b_sph, c_sph) block of pair item `it`
+SI_HD void si_g3_store(const OutDesc& od, const SiPairItem& it, int fa0, int fb0, int nsa, int nsb, int nm,
+                       long long col, int ia, int jb, int m, double val) {
+    if (od.mode == STORE_BLOCK) {
+        od.out[((long long)ia * nsb + jb) * nm + m] = val;
+    } else if (od.mode == STORE_3C_FULL) {
+        od.out[((long long)(fa0 + ia) * od.nbf + (fb0 + jb)) * od.ld + col + m] = val;
+        if (it.sa != it.sb) od.out[((long long)(fb0 + jb) * od.nbf + (fa0 + ia)) * od.ld + col + m] = val;
+    } else {
+        const long long row = it.swapped ? it.prow + (long long)jb * nsa + ia : it.prow + (long long)ia * nsb + jb;
+        od.out[row * od.ld + col + m] = val;
+    }
+}

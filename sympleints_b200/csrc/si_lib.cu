@@ -22,39 +22,14 @@
 #include <vector>
 
 #include "../../include/sympleints_b200.h"
+#include "si_g3.h"
 #include "si_machine.h"
 #include "si_program.h"
+#include "generated/g3_table.inc"
 
 // ---------------------------------------------------------------------------
 // device-side data
 // ---------------------------------------------------------------------------
-struct BasisDev {
-    const int* L;
-    const int* nprim;
-    const int* poff;
-    const int* foff;  // function offsets (sph or cart, chosen by the host)
-    const double* cen;
-    const double* exps;
-    const double* coef;
-};
-
-struct SiPairItem {
-    int sa, sb;       // shell indices; L(sa) >= L(sb)
-    int swapped;      // packed layout: 1 if sa is the column shell of the (i>=j) block
-    int pad;
-    long long prow;   // first row of the pair block in the packed 3-index layout
-};
-
-enum StoreMode { STORE_BLOCK = 0, STORE_MATRIX = 1, STORE_3C_FULL = 2, STORE_3C_PACKED = 3 };
-
-struct OutDesc {
-    double* out;
-    long long ld;           // matrix: nbf ; 3c: naux_local
-    long long comp_stride;  // matrix: nbf*nbf
-    long long nbf;
-    int mode;
-};
-
 __device__ __forceinline__ long long next_item(int* counter, int lane) {
     int v = 0;
     if (lane == 0) v = atomicAdd(counter, 1);
@@ -857,6 +832,48 @@ int si_coul(si_context* c, const si_basis* b, int sph, int normalize, int ncharg
     return rc;
 }
 
+// ---- generated class-specialised 3c2e kernels (codegen/gen3c2e.py) ----------------------------
+static const int* g3_find(int La, int Lb, int Lc) {
+    const int id = La * 100 + Lb * 10 + Lc;
+    const int n = (int)(sizeof(g3_table) / sizeof(g3_table[0]));
+    for (int i = 0; i < n; ++i)
+        if (g3_table[i][0] == id) return g3_table[i];
+    return nullptr;
+}
+static bool g3_disabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SI_FORCE_LUT");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+static void g3_fill_args(G3Args& ga, si_context* c, const BasisDev& orb, const BasisDev& aux, const SiPairItem* pairs,
+                         int npairs, const int* auxlist, int naux_c, int col_begin, const OutDesc& od, int* counter,
+                         int tpw) {
+    ga.orb = orb;
+    ga.aux = aux;
+    ga.pairs = pairs;
+    ga.npairs = npairs;
+    ga.auxlist = auxlist;
+    ga.naux_c = naux_c;
+    ga.col_begin = col_begin;
+    ga.groups_per_pair = (naux_c + tpw - 1) / tpw;
+    ga.ngroups = (long long)npairs * ga.groups_per_pair;
+    ga.od = od;
+    ga.counter = counter;
+    ga.boys = c->boys_dev;
+}
+static bool g3_config(const si_context* c, const int* g3, long long ngroups, int* grid, int* block, size_t* smem) {
+    const size_t per_warp = (size_t)g3[4] * g3[3] * sizeof(double);  // WSZ * TPW
+    int nw = (int)std::min<size_t>(4, (size_t)c->max_smem / per_warp);
+    if (nw < 1) return false;
+    *block = nw * 32;
+    *smem = per_warp * nw;
+    *grid = (int)std::max<long long>(1, std::min<long long>((ngroups + nw - 1) / nw, (long long)c->sm_count * 16));
+    return true;
+}
+
 int si_int3c2e(si_context* c, const si_basis* corb, const si_basis* caux, int sb, int se, int normalize, int layout,
                double* out_dev, size_t out_len, void* stream) {
     if (!c || !corb || !caux || !out_dev) return SI_ERR_ARG;
@@ -919,21 +936,35 @@ int si_int3c2e(si_context* c, const si_basis* corb, const si_basis* caux, int sb
         DevProgram* p;
         rc = get_program(c, SI_3C2E, job.pc->La, job.pc->Lb, job.Lc, 1, normalize, &p);
         if (rc) return rc;
-        size_t smem = 0;
-        int nw = pick_warps(c, p->dev, 4, &smem);
-        if (nw < 1) {
-            g_last_error = "class does not fit into shared memory";
-            return SI_ERR_INTERNAL;
-        }
         auto sp = span[job.Lc];
-        long long nitems = (long long)job.pc->n * sp.second;
-        int grid = (int)std::min<long long>((nitems + nw - 1) / nw, (long long)c->sm_count * 16);
         cudaStream_t s;
         rc = fan.stream(&s);
         if (rc) return rc;
         int* counter = c->d_counters + (c->next_counter++ % SI_NCOUNTERS);
-        k_3c2e<<<grid, nw * 32, smem, s>>>(p->dev, c->boys_dev, od_orb, od_aux, job.pc->d_items, job.pc->n,
-                                           d_list + sp.first, sp.second, col_begin, od, counter);
+        const int* g3 = g3_find(job.pc->La, job.pc->Lb, job.Lc);
+        if (g3 && normalize != SI_NORM_NONE && !g3_disabled()) {
+            G3Args ga;
+            g3_fill_args(ga, c, od_orb, od_aux, job.pc->d_items, job.pc->n, d_list + sp.first, sp.second, col_begin,
+                         od, counter, g3[3]);
+            int grid, block;
+            size_t smem;
+            if (!g3_config(c, g3, ga.ngroups, &grid, &block, &smem)) {
+                g_last_error = "generated class does not fit into shared memory";
+                return SI_ERR_INTERNAL;
+            }
+            if (g3_launch(g3[1], g3[0], ga, grid, block, smem, s)) return SI_ERR_INTERNAL;
+        } else {
+            size_t smem = 0;
+            int nw = pick_warps(c, p->dev, 4, &smem);
+            if (nw < 1) {
+                g_last_error = "class does not fit into shared memory";
+                return SI_ERR_INTERNAL;
+            }
+            long long nitems = (long long)job.pc->n * sp.second;
+            int grid = (int)std::min<long long>((nitems + nw - 1) / nw, (long long)c->sm_count * 16);
+            k_3c2e<<<grid, nw * 32, smem, s>>>(p->dev, c->boys_dev, od_orb, od_aux, job.pc->d_items, job.pc->n,
+                                               d_list + sp.first, sp.second, col_begin, od, counter);
+        }
         c->launches++;
         SI_CUDA(cudaGetLastError());
     }
@@ -1180,7 +1211,22 @@ int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int n
         bd.foff = nullptr;
         if (three) {
             BasisDev ad = basis_dev(xb, 1, normalize);
-            k_3c2e<<<1, 32, smem>>>(P, c->boys_dev, bd, ad, d_item, 1, nullptr, 1, 0, od, d_counter);
+            const int* g3 = g3_find(Ls[0], Ls[1], Lc);
+            if (g3 && normalize != SI_NORM_NONE && !g3_disabled()) {
+                int zero = 0, *d_list1 = nullptr;
+                e = cudaMalloc((void**)&d_list1, sizeof(int));
+                if (e == cudaSuccess) e = cudaMemcpy(d_list1, &zero, sizeof(int), cudaMemcpyHostToDevice);
+                G3Args ga;
+                g3_fill_args(ga, c, bd, ad, d_item, 1, d_list1, 1, 0, od, d_counter, g3[3]);
+                int grid, block;
+                size_t sm2;
+                if (e == cudaSuccess && g3_config(c, g3, ga.ngroups, &grid, &block, &sm2))
+                    g3_launch(g3[1], g3[0], ga, 1, 32, (size_t)g3[4] * g3[3] * sizeof(double), 0);
+                if (e == cudaSuccess) e = cudaDeviceSynchronize();
+                cudaFree(d_list1);
+            } else {
+                k_3c2e<<<1, 32, smem>>>(P, c->boys_dev, bd, ad, d_item, 1, nullptr, 1, 0, od, d_counter);
+            }
         } else if (key == SI_COUL) {
             double one = 1.0;
             double Rz[3] = {R ? R[0] : 0.0, R ? R[1] : 0.0, R ? R[2] : 0.0};

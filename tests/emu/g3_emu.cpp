@@ -1,0 +1,95 @@
+// TEST INFRASTRUCTURE ONLY -- warp emulation of the GENERATED 3c2e kernels on host threads.
+// 32 std::threads play the lanes of one warp; __syncwarp is a std::barrier.  The generated source
+// (tests/emu/g3_emu_classes.inc, written by codegen/gen3c2e.py:write_emu_source) is the same text
+// nvcc compiles for the GPU.
+#include <barrier>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "g3_emu_classes.inc"
+
+thread_local SiG3EmuWarp* si_g3_emu_warp = nullptr;
+thread_local int si_g3_emu_lane = 0;
+thread_local double* si_g3_emu_smem = nullptr;
+
+extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, const double* da, const double* A,
+                          int Kb, const double* bx, const double* db, const double* B, int naux, const int* Kc,
+                          const double* cx, const double* dc, const double* C /* naux*3 */,
+                          const double* boys_table, int nrows, int ncols, const double* xlarge_pref,
+                          double* result /* naux blocks, each (na, nb, nc) */) {
+    const int id = La * 100 + Lb * 10 + Lc;
+    const G3EmuClass* cls = nullptr;
+    for (int i = 0; i < g3_emu_nclasses; ++i)
+        if (g3_emu_classes[i].id == id) cls = &g3_emu_classes[i];
+    if (!cls) return 2;
+    // orbital "basis": shells 0 (a) and 1 (b); aux basis: naux shells of angular momentum Lc
+    int oL[2] = {La, Lb}, onp[2] = {Ka, Kb}, opoff[2] = {0, Ka}, ofoff[2] = {0, 2 * La + 1};
+    std::vector<double> ocen(6), oex, oco;
+    for (int d = 0; d < 3; ++d) {
+        ocen[d] = A[d];
+        ocen[3 + d] = B[d];
+    }
+    oex.insert(oex.end(), ax, ax + Ka);
+    oex.insert(oex.end(), bx, bx + Kb);
+    oco.insert(oco.end(), da, da + Ka);
+    oco.insert(oco.end(), db, db + Kb);
+    std::vector<int> aL(naux, Lc), anp(Kc, Kc + naux), apoff(naux), afoff(naux), alist(naux);
+    int np = 0;
+    for (int i = 0; i < naux; ++i) {
+        apoff[i] = np;
+        np += Kc[i];
+        afoff[i] = i * (2 * Lc + 1);
+        alist[i] = i;
+    }
+    G3Args args;
+    memset(&args, 0, sizeof(args));
+    args.orb = BasisDev{oL, onp, opoff, ofoff, ocen.data(), oex.data(), oco.data()};
+    args.aux = BasisDev{aL.data(), anp.data(), apoff.data(), afoff.data(), C, cx, dc};
+    SiPairItem item;
+    memset(&item, 0, sizeof(item));
+    item.sa = 0;
+    item.sb = 1;
+    args.pairs = &item;
+    args.npairs = 1;
+    args.auxlist = alist.data();
+    args.naux_c = naux;
+    args.col_begin = 0;
+    args.groups_per_pair = (naux + cls->tpw - 1) / cls->tpw;
+    args.ngroups = args.groups_per_pair;
+    const int na = 2 * La + 1, nb = 2 * Lb + 1, nc = 2 * Lc + 1;
+    // full layout of a 2-shell orbital basis: (nbf, nbf, naux*nc); we extract the (a, b) block afterwards
+    const int nbf = na + nb;
+    std::vector<double> full((size_t)nbf * nbf * naux * nc, 0.0);
+    args.od.out = full.data();
+    args.od.ld = (long long)naux * nc;
+    args.od.nbf = nbf;
+    args.od.mode = STORE_3C_FULL;
+    int counter = 0;
+    args.counter = &counter;
+    args.boys.table = boys_table;
+    args.boys.xlarge_pref = xlarge_pref;
+    args.boys.nrows = nrows;
+    args.boys.ncols = ncols;
+    std::vector<double> smem((size_t)cls->wsz * cls->tpw, 0.0);
+    std::barrier<> bar(32);
+    SiG3EmuWarp warp;
+    warp.bar = &bar;
+    std::vector<std::thread> th;
+    for (int lane = 0; lane < 32; ++lane)
+        th.emplace_back([&, lane]() {
+            si_g3_emu_warp = &warp;
+            si_g3_emu_lane = lane;
+            si_g3_emu_smem = smem.data();
+            cls->body(args, lane, smem.data());
+        });
+    for (auto& t : th) t.join();
+    for (int k = 0; k < naux; ++k)
+        for (int i = 0; i < na; ++i)
+            for (int j = 0; j < nb; ++j)
+                for (int m = 0; m < nc; ++m)
+                    result[(((size_t)k * na + i) * nb + j) * nc + m] =
+                        full[((size_t)i * nbf + (na + j)) * args.od.ld + (size_t)k * nc + m];
+    return 0;
+}

@@ -90,3 +90,50 @@ def emu_eval(key, La, Lb, Lc, shell_a, shell_b, shell_c=None, R=None, q=None, sp
         _p(R), ncharge, _p(q), _p(table), table.shape[0], table.shape[1], _p(pref), _p(res))
     assert rc == 0
     return res
+
+
+# ---- warp emulator of the GENERATED 3c2e kernels (tests/emu/g3_emu.cpp) ------------------------
+G3_EMU_CLASSES = [(0, 0, 0), (0, 0, 2), (1, 0, 1), (1, 1, 0), (1, 1, 2), (2, 0, 3), (2, 1, 2), (2, 2, 1),
+                  (3, 1, 4), (3, 3, 2), (4, 2, 5), (4, 4, 5)]
+_G3 = None
+
+
+def g3_lib():
+    global _G3
+    if _G3 is not None:
+        return _G3
+    from sympleints_b200.codegen import gen3c2e
+
+    inc = HERE / "emu" / "g3_emu_classes.inc"
+    gen3c2e.write_emu_source(str(inc), G3_EMU_CLASSES)
+    so = HERE / "emu" / "libg3_emu.so"
+    deps = [inc, HERE / "emu" / "g3_emu.cpp", REPO / "sympleints_b200" / "csrc" / "si_g3.h",
+            REPO / "sympleints_b200" / "csrc" / "si_machine.h"]
+    if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-o", str(so),
+                               str(HERE / "emu" / "g3_emu.cpp")])
+    _G3 = ctypes.CDLL(str(so))
+    return _G3
+
+
+def g3_eval(La, Lb, Lc, shell_a, shell_b, aux_shells, table=None):
+    """aux_shells: list of (exps, coeffs, center) all with angular momentum Lc.  Returns
+    array (naux, na, nb, nc)."""
+    if table is None:
+        from oracle import boys as oboys
+        table = oboys.table()
+    table = np.ascontiguousarray(table)
+    pref = xlarge_pref(table.shape[0] - 7)
+    ax, da, A = [np.ascontiguousarray(x, dtype=float) for x in shell_a]
+    bx, db, B = [np.ascontiguousarray(x, dtype=float) for x in shell_b]
+    Kc = np.array([len(s[0]) for s in aux_shells], dtype=np.int32)
+    cx = np.ascontiguousarray(np.concatenate([s[0] for s in aux_shells]), dtype=float)
+    dc = np.ascontiguousarray(np.concatenate([s[1] for s in aux_shells]), dtype=float)
+    C = np.ascontiguousarray(np.array([s[2] for s in aux_shells], dtype=float).reshape(-1, 3))
+    naux = len(aux_shells)
+    res = np.zeros((naux, 2 * La + 1, 2 * Lb + 1, 2 * Lc + 1))
+    rc = g3_lib().g3emu_eval(La, Lb, Lc, ax.size, _p(ax), _p(da), _p(A), bx.size, _p(bx), _p(db), _p(B), naux,
+                             Kc.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _p(cx), _p(dc), _p(C), _p(table),
+                             table.shape[0], table.shape[1], _p(pref), _p(res))
+    assert rc == 0, rc
+    return res
