@@ -151,7 +151,7 @@ class ClassGen:
         self.nca, self.ncb = ncart(La), ncart(Lb)
         self.nsa, self.nsb = nsph(La), nsph(Lb)
         if ept is None:
-            ept = min(32, pow2ceil(max(1, (self.n_ap + 1) // 2)))
+            ept = min(32, pow2ceil(max(1, (self.n_ap + 3) // 4)))
         self.EPT = ept
         self.TPW = 32 // ept
         self.name = f"{La}{Lb}{Lc}"
@@ -219,6 +219,11 @@ class ClassGen:
 
     def nslots(self, count):
         return (count + self.EPT - 1) // self.EPT
+
+    def sync(self, comment=""):
+        """Warp barrier between stages; not needed when every lane owns its whole tuple."""
+        if self.EPT > 1:
+            self.emit("si_g3_syncwarp();" + (f"   // {comment}" if comment else ""))
 
     # ---- per-class metadata tables ----------------------------------------------------
     def vrr_meta(self):
@@ -308,8 +313,9 @@ class ClassGen:
         nsl_d = self.nslots(self.NA)
         if Lc > 0:
             for s in range(nsl_d):
-                E(f"int dd_{s}, ds_{s}; double dfx_{s}, dfy_{s}, dfz_{s}; {{ int f = q + EPT * {s}; if (f >= {self.NA}) f = {self.NA - 1}; "
-                  f"int v = g3_dd_{name}[f]; int w = g3_df_{name}[f]; dd_{s} = v; ds_{s} = (v >> 24) & 0xF; "
+                E(f"int nx_{s}, ny_{s}, nz_{s}, ds_{s}; double dfx_{s}, dfy_{s}, dfz_{s}; {{ int f = q + EPT * {s}; if (f >= {self.NA}) f = {self.NA - 1}; "
+                  f"int v = g3_dd_{name}[f]; int w = g3_df_{name}[f]; ds_{s} = (v >> 24) & 0xF; "
+                  f"nx_{s} = f - (v & 0xFF); ny_{s} = f - ((v >> 8) & 0xFF); nz_{s} = f - ((v >> 16) & 0xFF); "
                   f"dfx_{s} = (double)(w & 0xF); dfy_{s} = (double)((w >> 4) & 0xF); dfz_{s} = (double)((w >> 8) & 0xF); }}")
         E("")
         # ---- work loop over tuple groups
@@ -336,29 +342,31 @@ class ClassGen:
         E("const double ax = A.orb.exps[pa0 + ia], da = A.orb.coef[pa0 + ia];")
         self.open("for (int ib = 0; ib < Kb; ++ib)")
         E("const double bx = A.orb.exps[pb0 + ib], db = A.orb.coef[pb0 + ib];")
-        E("const double p = ax + bx, oop = 1.0 / p, mu = ax * bx * oop;")
-        E("double P[3], PA[3]; double r2ab = 0.0;")
-        self.open("for (int d = 0; d < 3; ++d)")
-        E("P[d] = (ax * Ax[d] + bx * Bx[d]) * oop; PA[d] = P[d] - Ax[d]; r2ab += AB[d] * AB[d];")
-        self.close()
-        E("const double Kab = exp(-mu * r2ab) * da * db;")
+        E("// primitive-pair data precomputed by the host shell-batcher: p, 1/p, P[3], PA[3], exp(-mu AB^2) da db")
+        E("const double* pp = A.ppair + (size_t)(it.ppoff + ia * Kb + ib) * 9;")
+        E("const double p = pp[0], oop = pp[1];")
+        E("const double P[3] = {pp[2], pp[3], pp[4]};")
+        E("const double PA[3] = {pp[5], pp[6], pp[7]};")
+        E("const double Kab = pp[8];")
+        E("(void)ax; (void)bx; (void)da; (void)db;")
         self.open("for (int ik = 0; ik < Kc_max; ++ik)")
         E("// tuples with fewer aux primitives repeat their last one with zero weight")
         E("const int ikk = ik < Kc ? ik : Kc - 1;")
         E("const double cx = A.aux.exps[pc0 + ikk], dc = ik < Kc ? A.aux.coef[pc0 + ikk] : 0.0;")
+        E("const double ocx = 1.0 / cx;")
         self._emit_primitive()
         E("first = false;")
         self.close()  # ik
         self.close()  # ib
         self.close()  # ia
-        E("si_g3_syncwarp();")
+        self.sync()
         self._emit_c2s_c()
-        E("si_g3_syncwarp();")
+        self.sync()
         if Lb > 0:
             self._emit_hrr_c2sb()
-            E("si_g3_syncwarp();")
+            self.sync()
         self._emit_c2s_a_store()
-        E("si_g3_syncwarp();")
+        self.sync()
         self.close()  # for(;;)
         self.close()  # function
         E("")
@@ -377,21 +385,23 @@ class ClassGen:
         E = self.emit
         vm_n = self.vrr_meta()
         E("const double pc_ = p + cx;")
-        E("const double rho = p * cx / pc_;")
-        E("const double rho_p = rho * oop;")
+        E("const double rpc = 1.0 / pc_;")
+        E("const double rho = p * cx * rpc;")
+        E("const double rho_p = cx * rpc;          // rho / p")
         E("double PC[3]; double r2pc = 0.0;")
         self.open("for (int d = 0; d < 3; ++d)")
         E("PC[d] = P[d] - Cx[d]; r2pc += PC[d] * PC[d];")
         self.close()
         E("const double T = rho * r2pc;")
-        E("const double pref = 2.0 * SI_PI_25 / (sqrt(pc_) * p * cx) * Kab * dc;")
+        E("// 2 pi^2.5 / (sqrt(p+c) p c) * K_ab * d_c ;  1/sqrt(p+c) = sqrt(p+c) / (p+c)")
+        E("const double pref = 2.0 * SI_PI_25 * (sqrt(pc_) * rpc) * oop * ocx * Kab * dc;")
         E("const double oo2p = 0.5 * oop, c2 = -0.5 * oop * rho_p;")
-        E("const double beta = 0.5 / pc_;      // (rho/c)/(2p)")
+        E("const double beta = 0.5 * rpc;      // (rho/c)/(2p)")
         E("const double binv = 2.0 * pc_;")
-        E("const double rho_c = rho / cx;")
+        E("const double rho_c = p * rpc;       // rho / c")
         E("const double alx = rho_c * PC[0], aly = rho_c * PC[1], alz = rho_c * PC[2];")
         E("(void)alx; (void)aly; (void)alz; (void)beta; (void)binv;")
-        E("si_g3_syncwarp();   // previous primitive's readers are done")
+        self.sync("previous primitive's readers are done")
         # scalars to shared memory (lane q==0 of the tuple)
         self.open("if (q == 0)")
         for d in range(3):
@@ -410,7 +420,7 @@ class ClassGen:
         # note: V(0,jn,0) are contiguous since ncart(0)=1
         for jn in range(nb):
             assert self.V_OFF[(0, jn)] == self.V_OFF[(0, 0)] + jn
-        E("si_g3_syncwarp();")
+        self.sync()
         # ---- VRR shells
         for n in range(1, L + 1):
             nc = ncart(n)
@@ -439,7 +449,7 @@ class ClassGen:
                         E(f"W[{self.V_OFF[(n, jn)]} + k_] = fma(pa_, u0, cp_ * u1);")
                     E("u0 = u1;")
                 self.close()
-            E("si_g3_syncwarp();")
+            self.sync()
         # ---- D-tree
         if Lc == 0:
             # X[0][a'] (+)= V(n,0,k) for shells La..L
@@ -466,7 +476,7 @@ class ClassGen:
             E("bq *= binv;")
         self.ind -= 1
         E("}")
-        E("si_g3_syncwarp();")
+        self.sync()
         # DFS over monomials; direction sequences non-decreasing (x.., y.., z..)
         nsl = self.nslots(self.NA)
         # per-slot: own root values + beta powers for the leaves
@@ -501,7 +511,7 @@ class ClassGen:
                     E(f"const int f = q + EPT * {s};")
                     if not full:
                         self.open(f"if (f >= {lo2} && f < {self.NA})")
-                    E(f"const double nb_ = W[{self.D_OFF[level]} + f - ((dd_{s} >> {8 * d}) & 0xFF)];")
+                    E(f"const double nb_ = W[{self.D_OFF[level]} + {'nx ny nz'.split()[d]}_{s}];")
                     E(f"const double v_ = fma({dfn[d]}_{s}, nb_, {al[d]} * r{level}_{s});")
                     if leaf:
                         ci = cidx(c2)
@@ -514,9 +524,9 @@ class ClassGen:
                     self.ind -= 1
                     E("}")
                 if not leaf:
-                    E("si_g3_syncwarp();")
+                    self.sync()
                     rec(c2, lev2, d)
-                    E("si_g3_syncwarp();   // children done before the array is overwritten")
+                    self.sync("children done before the array is overwritten")
                 self.close()
 
         self.open("")

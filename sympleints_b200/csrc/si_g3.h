@@ -23,7 +23,7 @@ struct BasisDev {
 struct SiPairItem {
     int sa, sb;       // shell indices; L(sa) >= L(sb)
     int swapped;      // packed layout: 1 if sa is the column shell of the (i>=j) block
-    int pad;
+    int ppoff;        // first primitive pair of this shell pair in the precomputed pair-data array
     long long prow;   // first row of the pair block in the packed 3-index layout
 };
 
@@ -40,6 +40,7 @@ struct OutDesc {
 struct G3Args {
     BasisDev orb, aux;
     const SiPairItem* pairs;
+    const double* ppair;  // 9 doubles per primitive pair: p, 1/p, P[3], PA[3], exp(-mu AB^2) da db
     int npairs;
     const int* auxlist;   // aux shells of this class (same Lc)
     int naux_c;

@@ -346,6 +346,8 @@ struct si_basis {
         int n = 0;
         SiPairItem* d_items = nullptr;
     };
+    // precomputed primitive-pair data (9 doubles each) for coef / coef_pgto
+    double* d_ppair[2] = {nullptr, nullptr};
     std::vector<PairClass> pair_classes;
     // aux shells by angular momentum
     struct AuxClass {
@@ -650,6 +652,8 @@ int si_basis_destroy(si_basis* b) {
     cudaFree(b->d_coef);
     cudaFree(b->d_coef_pgto);
     for (auto& pc : b->pair_classes) cudaFree(pc.d_items);
+    cudaFree(b->d_ppair[0]);
+    cudaFree(b->d_ppair[1]);
     delete b;
     return SI_OK;
 }
@@ -681,6 +685,42 @@ static int build_pair_classes(si_basis* b) {
             prow += (long long)si_nsph(b->L[i]) * si_nsph(b->L[j]);
             cls[{b->L[it.sa], b->L[it.sb]}].push_back(it);
         }
+    // primitive-pair data, shared by all classes (offset per shell pair)
+    {
+        size_t npp = 0;
+        for (auto& kv : cls)
+            for (auto& it : kv.second) {
+                it.ppoff = (int)npp;
+                npp += (size_t)b->nprim[it.sa] * b->nprim[it.sb];
+            }
+        for (int variant = 0; variant < 2; ++variant) {
+            const std::vector<double>& co = variant ? b->coef_pgto : b->coef;
+            std::vector<double> pp(npp * 9);
+            for (auto& kv : cls)
+                for (auto& it : kv.second) {
+                    const int Ka = b->nprim[it.sa], Kb = b->nprim[it.sb];
+                    const double* A = &b->cen[3 * it.sa];
+                    const double* B = &b->cen[3 * it.sb];
+                    for (int i = 0; i < Ka; ++i)
+                        for (int j = 0; j < Kb; ++j) {
+                            double* q = &pp[((size_t)it.ppoff + (size_t)i * Kb + j) * 9];
+                            const double ax = b->exps[b->poff[it.sa] + i], bx = b->exps[b->poff[it.sb] + j];
+                            const double p = ax + bx, oop = 1.0 / p, mu = ax * bx * oop;
+                            double r2 = 0.0;
+                            q[0] = p;
+                            q[1] = oop;
+                            for (int d = 0; d < 3; ++d) {
+                                q[2 + d] = (ax * A[d] + bx * B[d]) * oop;
+                                q[5 + d] = q[2 + d] - A[d];
+                                r2 += (A[d] - B[d]) * (A[d] - B[d]);
+                            }
+                            q[8] = std::exp(-mu * r2) * co[b->poff[it.sa] + i] * co[b->poff[it.sb] + j];
+                        }
+                }
+            SI_CUDA(cudaMalloc((void**)&b->d_ppair[variant], std::max<size_t>(pp.size() * sizeof(double), 8)));
+            SI_CUDA(cudaMemcpy(b->d_ppair[variant], pp.data(), pp.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
     for (auto& kv : cls) {
         auto& v = kv.second;
         std::stable_sort(v.begin(), v.end(), [&](const SiPairItem& x, const SiPairItem& y) {
@@ -849,11 +889,12 @@ static bool g3_disabled() {
     return v == 1;
 }
 static void g3_fill_args(G3Args& ga, si_context* c, const BasisDev& orb, const BasisDev& aux, const SiPairItem* pairs,
-                         int npairs, const int* auxlist, int naux_c, int col_begin, const OutDesc& od, int* counter,
+                         const double* ppair, int npairs, const int* auxlist, int naux_c, int col_begin, const OutDesc& od, int* counter,
                          int tpw) {
     ga.orb = orb;
     ga.aux = aux;
     ga.pairs = pairs;
+    ga.ppair = ppair;
     ga.npairs = npairs;
     ga.auxlist = auxlist;
     ga.naux_c = naux_c;
@@ -944,7 +985,7 @@ int si_int3c2e(si_context* c, const si_basis* corb, const si_basis* caux, int sb
         const int* g3 = g3_find(job.pc->La, job.pc->Lb, job.Lc);
         if (g3 && normalize != SI_NORM_NONE && !g3_disabled()) {
             G3Args ga;
-            g3_fill_args(ga, c, od_orb, od_aux, job.pc->d_items, job.pc->n, d_list + sp.first, sp.second, col_begin,
+            g3_fill_args(ga, c, od_orb, od_aux, job.pc->d_items, orb->d_ppair[normalize == SI_NORM_PGTO ? 1 : 0], job.pc->n, d_list + sp.first, sp.second, col_begin,
                          od, counter, g3[3]);
             int grid, block;
             size_t smem;
@@ -1217,13 +1258,39 @@ int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int n
                 e = cudaMalloc((void**)&d_list1, sizeof(int));
                 if (e == cudaSuccess) e = cudaMemcpy(d_list1, &zero, sizeof(int), cudaMemcpyHostToDevice);
                 G3Args ga;
-                g3_fill_args(ga, c, bd, ad, d_item, 1, d_list1, 1, 0, od, d_counter, g3[3]);
+                // primitive-pair data of the single (a = shell 0, b = shell 1) item
+                std::vector<double> pp((size_t)nps[0] * nps[1] * 9);
+                {
+                    const std::vector<double>& co = (normalize == SI_NORM_PGTO) ? ob->coef_pgto : ob->coef;
+                    for (int i = 0; i < nps[0]; ++i)
+                        for (int j = 0; j < nps[1]; ++j) {
+                            double* q = &pp[((size_t)i * nps[1] + j) * 9];
+                            const double ax_ = ob->exps[i], bx_ = ob->exps[nps[0] + j];
+                            const double p_ = ax_ + bx_, oop = 1.0 / p_, mu = ax_ * bx_ * oop;
+                            double r2 = 0.0;
+                            q[0] = p_;
+                            q[1] = oop;
+                            for (int d = 0; d < 3; ++d) {
+                                q[2 + d] = (ax_ * A_[d] + bx_ * B_[d]) * oop;
+                                q[5 + d] = q[2 + d] - A_[d];
+                                r2 += (A_[d] - B_[d]) * (A_[d] - B_[d]);
+                            }
+                            q[8] = std::exp(-mu * r2) * co[i] * co[nps[0] + j];
+                        }
+                }
+                double* d_pp = nullptr;
+                if (e == cudaSuccess) e = cudaMalloc((void**)&d_pp, pp.size() * sizeof(double));
+                if (e == cudaSuccess) e = cudaMemcpy(d_pp, pp.data(), pp.size() * sizeof(double), cudaMemcpyHostToDevice);
+                item.ppoff = 0;
+                if (e == cudaSuccess) e = cudaMemcpy(d_item, &item, sizeof(item), cudaMemcpyHostToDevice);
+                g3_fill_args(ga, c, bd, ad, d_item, d_pp, 1, d_list1, 1, 0, od, d_counter, g3[3]);
                 int grid, block;
                 size_t sm2;
                 if (e == cudaSuccess && g3_config(c, g3, ga.ngroups, &grid, &block, &sm2))
                     g3_launch(g3[1], g3[0], ga, 1, 32, (size_t)g3[4] * g3[3] * sizeof(double), 0);
                 if (e == cudaSuccess) e = cudaDeviceSynchronize();
                 cudaFree(d_list1);
+                cudaFree(d_pp);
             } else {
                 k_3c2e<<<1, 32, smem>>>(P, c->boys_dev, bd, ad, d_item, 1, nullptr, 1, 0, od, d_counter);
             }

@@ -3,6 +3,7 @@
 // (tests/emu/g3_emu_classes.inc, written by codegen/gen3c2e.py:write_emu_source) is the same text
 // nvcc compiles for the GPU.
 #include <barrier>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <thread>
@@ -51,6 +52,22 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
     memset(&item, 0, sizeof(item));
     item.sa = 0;
     item.sb = 1;
+    std::vector<double> pp((size_t)Ka * Kb * 9);
+    for (int i = 0; i < Ka; ++i)
+        for (int j = 0; j < Kb; ++j) {
+            double* q = &pp[(size_t)(i * Kb + j) * 9];
+            double p = ax[i] + bx[j], oop = 1.0 / p, mu = ax[i] * bx[j] * oop, r2 = 0.0;
+            q[0] = p;
+            q[1] = oop;
+            for (int d = 0; d < 3; ++d) {
+                q[2 + d] = (ax[i] * A[d] + bx[j] * B[d]) * oop;
+                q[5 + d] = q[2 + d] - A[d];
+                r2 += (A[d] - B[d]) * (A[d] - B[d]);
+            }
+            q[8] = exp(-mu * r2) * da[i] * db[j];
+        }
+    item.ppoff = 0;
+    args.ppair = pp.data();
     args.pairs = &item;
     args.npairs = 1;
     args.auxlist = alist.data();
