@@ -22,6 +22,19 @@ from __future__ import annotations
 import math
 from fractions import Fraction
 
+import json as _json
+import os as _os
+
+# per-class tuning (lanes per tuple, min CTAs/SM for __launch_bounds__) found by scripts/tune_g3.py
+DEFAULT_MB = int(_os.environ.get("SI_G3_MB", "1"))
+_TUNE_FILE = _os.path.join(_os.path.dirname(__file__), "tuning.json")
+TUNING = {}
+if _os.path.exists(_TUNE_FILE) and not _os.environ.get("SI_G3_NO_TUNING"):
+    TUNING = _json.load(open(_TUNE_FILE))
+if _os.environ.get("SI_G3_EPT_SHIFT"):
+    pass
+
+
 
 # ----------------------------------------------------------------------------------------
 # small helpers (orderings identical to sympleints/helpers.py:42-49)
@@ -140,8 +153,14 @@ def pow2ceil(n):
 class ClassGen:
     """Emit the device function + kernel for one class."""
 
-    def __init__(self, La, Lb, Lc, ept=None):
+    def __init__(self, La, Lb, Lc, ept=None, mb=None):
         assert La >= Lb
+        tune = TUNING.get(f"{La}{Lb}{Lc}", {})
+        if ept is None:
+            ept = tune.get("ept")
+        if mb is None:
+            mb = tune.get("mb", DEFAULT_MB)
+        self.MB = mb
         self.La, self.Lb, self.Lc = La, Lb, Lc
         self.L = L = La + Lb
         self.NA = off(L + 1)                 # flat a size, shells 0..L
@@ -151,7 +170,12 @@ class ClassGen:
         self.nca, self.ncb = ncart(La), ncart(Lb)
         self.nsa, self.nsb = nsph(La), nsph(Lb)
         if ept is None:
-            ept = min(32, pow2ceil(max(1, (self.n_ap + 3) // 4)))
+            ept = min(32, pow2ceil(max(1, (self.n_ap + 1) // 2)))
+            sh = int(_os.environ.get("SI_G3_EPT_SHIFT", "0"))
+            if sh < 0:
+                ept = max(1, ept >> (-sh))
+            elif sh > 0:
+                ept = min(32, ept << sh)
         self.EPT = ept
         self.TPW = 32 // ept
         self.name = f"{La}{Lb}{Lc}"
@@ -171,10 +195,15 @@ class ClassGen:
         o += 6 + (L + 1)
         if o % 2:
             o += 1
-        # X[c][a'] persistent over primitives
-        self.X_OFF = o
-        o += self.ncc * self.n_ap
-        x_end = o
+        # Y[m][a'] persistent over primitives: the leaves of the aux recurrence are folded straight
+        # into the spherical components (C2S on c), so no Cartesian [a0|c] block is ever stored
+        self.YS = self.n_ap | 1                    # odd stride between m rows of Y
+        self.ZS = (self.nca * self.nsb) | 1        # odd stride between m slabs of Z
+        if self.Lb == 0:
+            self.ZS = self.YS
+        self.Y_OFF = o
+        o += self.nm * self.YS
+        prim_start = o
         # primitive temporaries
         self.V_OFF = {}
         for n in range(L + 1):
@@ -187,20 +216,14 @@ class ClassGen:
             self.D_OFF[lev] = o - off(self.amin(lev))   # address of flat index f is D_OFF[lev] + f
             o += self.NA - off(self.amin(lev))
         prim_end = o
-        # contracted phase: Y[m][a'] over the primitive temporaries, Z over X (or after Y)
-        self.Y_OFF = x_end
-        y_end = x_end + self.nm * self.n_ap
-        zsize = self.nm * self.nca * self.nsb
+        # contracted phase: Z[m][a][jb] over the (dead) primitive temporaries
         if self.Lb == 0:
             self.Z_OFF = self.Y_OFF     # Z == Y (n_ap == nca, nsb == 1)
-            z_end = y_end
-        elif zsize <= x_end - self.X_OFF:
-            self.Z_OFF = self.X_OFF
-            z_end = y_end
+            z_end = prim_start
         else:
-            self.Z_OFF = y_end
-            z_end = y_end + zsize
-        w = max(prim_end, y_end, z_end)
+            self.Z_OFF = prim_start
+            z_end = prim_start + self.nm * self.ZS
+        w = max(prim_end, z_end)
         if w % 2 == 0:
             w += 1               # odd stride: conflict-free when several tuples share a warp
         self.WSZ = w
@@ -319,9 +342,12 @@ class ClassGen:
                   f"dfx_{s} = (double)(w & 0xF); dfy_{s} = (double)((w >> 4) & 0xF); dfz_{s} = (double)((w >> 8) & 0xF); }}")
         E("")
         # ---- work loop over tuple groups
+        E("// the next group index is fetched one iteration ahead so that the atomic's round trip is hidden")
+        E("long long grp_next = si_g3_next_group(A.counter, lane);")
         self.open("for (;;)")
-        E("long long grp = si_g3_next_group(A.counter, lane);")
+        E("const long long grp = grp_next;")
         E("if (grp >= A.ngroups) break;")
+        E("grp_next = si_g3_fetch_group(A.counter, lane);   // raw atomic result of lane 0, broadcast at the loop end")
         E("// group -> (pair, first aux of the group); tuples beyond the run end recompute the last valid one")
         E("const int ip = (int)(grp / A.groups_per_pair);")
         E("const int gi = (int)(grp - (long long)ip * A.groups_per_pair);")
@@ -360,18 +386,17 @@ class ClassGen:
         self.close()  # ib
         self.close()  # ia
         self.sync()
-        self._emit_c2s_c()
-        self.sync()
         if Lb > 0:
             self._emit_hrr_c2sb()
             self.sync()
         self._emit_c2s_a_store()
+        E("grp_next = si_g3_bcast_group(grp_next);")
         self.sync()
         self.close()  # for(;;)
         self.close()  # function
         E("")
         # kernel wrapper
-        E(f"SI_G3_GLOBAL void g3_kernel_{name}(G3Args A) {{")
+        E(f"SI_G3_GLOBAL({self.MB}) void g3_kernel_{name}(G3Args A) {{")
         E("    SI_G3_KERNEL_PROLOGUE")
         E(f"    g3_body_{name}(A, g3_lane, g3_smem + (size_t)g3_warp * {self.WSZ * TPW});")
         E("}")
@@ -452,15 +477,15 @@ class ClassGen:
             self.sync()
         # ---- D-tree
         if Lc == 0:
-            # X[0][a'] (+)= V(n,0,k) for shells La..L
+            # Y[0][a'] (+)= V(n,0,k) for shells La..L   (C2S of an s function is the identity)
             for n in range(La, L + 1):
                 nc = ncart(n)
                 for s in range(self.nslots(nc)):
                     partial = (s + 1) * EPT > nc
                     self.open(f"if (q + EPT * {s} < {nc})" if partial else "")
-                    xa = self.X_OFF + off(n) - off(La)
+                    ya = self.Y_OFF + off(n) - off(La)
                     E(f"const int k_ = q + EPT * {s}; const double v_ = W[{self.V_OFF[(n, 0)]} + k_];")
-                    E(f"if (first) W[{xa} + k_] = v_; else W[{xa} + k_] += v_;")
+                    E(f"if (first) W[{ya} + k_] = v_; else W[{ya} + k_] += v_;")
                     self.close()
             return
         # root: h[f] = V(n, 0, k) * binv^n for shells amin(0)..L, stored at D_OFF[0] + f
@@ -487,7 +512,9 @@ class ClassGen:
             E(f"const double bp_{s} = W[{self.S_BPOW} + ds_{s}];")
         al = ["alx", "aly", "alz"]
         dfn = ["dfx", "dfy", "dfz"]
-        ccomps = cart_order(Lc)
+        Mc = cart2sph(Lc)
+        fc = lmn_factors(Lc)
+        seen = set()     # (m, slot) pairs that already received their first contribution
 
         def rec(c, level, lastd):
             # values of node c are in registers r{level}_{s}; its array is at D_OFF[level]
@@ -515,8 +542,17 @@ class ClassGen:
                     E(f"const double v_ = fma({dfn[d]}_{s}, nb_, {al[d]} * r{level}_{s});")
                     if leaf:
                         ci = cidx(c2)
-                        xa = self.X_OFF + ci * self.n_ap - off(La)
-                        E(f"if (first) W[{xa} + f] = bp_{s} * v_; else W[{xa} + f] = fma(bp_{s}, v_, W[{xa} + f]);")
+                        E(f"const double t_ = bp_{s} * v_;")
+                        for m in range(self.nm):
+                            if Mc[m][ci] == 0.0:
+                                continue
+                            coef = lit(Mc[m][ci] * fc[ci])
+                            ya = self.Y_OFF + m * self.YS - off(La)
+                            if (m, s) not in seen:
+                                seen.add((m, s))
+                                E(f"if (first) W[{ya} + f] = {coef} * t_; else W[{ya} + f] = fma({coef}, t_, W[{ya} + f]);")
+                            else:
+                                E(f"W[{ya} + f] = fma({coef}, t_, W[{ya} + f]);")
                     else:
                         E(f"r{lev2}_{s} = v_; W[{self.D_OFF[lev2]} + f] = v_;")
                     if not full:
@@ -555,7 +591,7 @@ class ClassGen:
                 E(f"const double y{m} = {expr};")
             # stores after all loads (Y may not alias X: different regions)
             for m in range(self.nm):
-                E(f"W[{self.Y_OFF + m * n_ap} + f_] = y{m};")
+                E(f"W[{self.Y_OFF + m * self.YS} + f_] = y{m};")
             self.close()
 
     # ---- HRR tile per (target a, m) + C2S(b): Z[m][a][jb] ---------------------------------
@@ -595,7 +631,7 @@ class ClassGen:
         self.open(f"for (int item = q; item < {nit}; item += EPT)")
         E(f"const int ai = item / {nm}, m = item - ai * {nm};")
         E("int ia_ = 0; while ((ia_ + 1) * (ia_ + 2) / 2 <= ai) ++ia_;   // row of the target a (l = La - ia_)")
-        E(f"const int yb = {self.Y_OFF} + m * {n_ap} + ai;")
+        E(f"const int yb = {self.Y_OFF} + m * {self.YS} + ai;")
         for ik in range(Lb + 1):
             E(f"const int yb{ik} = yb + ia_ * {ik};")
         # inputs: idx(a+k) - idx-base: off(La+|k|)-off(La) + row(ik) + nz_k + ia*ik   (+ ai)
@@ -617,7 +653,7 @@ class ClassGen:
                 if Mb[jb][j] == 0.0:
                     continue
                 expr = f"{lit(coef)} * {targets[j]}" if expr is None else f"fma({lit(coef)}, {targets[j]}, {expr})"
-            E(f"W[{self.Z_OFF} + (m * {nca} + ai) * {nsb} + {jb}] = {expr};")
+            E(f"W[{self.Z_OFF} + m * {self.ZS} + ai * {nsb} + {jb}] = {expr};")
         self.close()
 
     # ---- C2S(a) + global store --------------------------------------------------------------
@@ -633,7 +669,7 @@ class ClassGen:
         self.open(f"for (int item = q; item < {nit}; item += EPT)")
         E(f"const int jb = item / {nm}, m = item - jb * {nm};")
         for a in range(nca):
-            E(f"const double z{a} = W[{self.Z_OFF} + (m * {nca} + {a}) * {nsb} + jb];")
+            E(f"const double z{a} = W[{self.Z_OFF} + m * {self.ZS} + {a * nsb} + jb];")
         for ia in range(nsa):
             expr = None
             for a in range(nca):

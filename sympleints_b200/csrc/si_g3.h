@@ -64,7 +64,7 @@ extern thread_local SiG3EmuWarp* si_g3_emu_warp;
 extern thread_local int si_g3_emu_lane;
 #define __device__
 #define SI_G3_DEV static inline
-#define SI_G3_GLOBAL static inline
+#define SI_G3_GLOBAL(mb) static inline
 #define SI_G3_KERNEL_PROLOGUE                                   \
     extern thread_local double* si_g3_emu_smem;                 \
     double* g3_smem = si_g3_emu_smem;                           \
@@ -77,6 +77,16 @@ static inline long long si_g3_next_group(int* counter, int lane) {
     si_g3_syncwarp();
     return v;
 }
+static inline long long si_g3_fetch_group(int* counter, int lane) {
+    return lane == 0 ? (long long)__atomic_fetch_add(counter, 1, __ATOMIC_SEQ_CST) : 0;
+}
+static inline long long si_g3_bcast_group(long long v) {
+    if (si_g3_emu_lane == 0) si_g3_emu_warp->xchg[0] = v;
+    si_g3_syncwarp();
+    long long r = si_g3_emu_warp->xchg[0];
+    si_g3_syncwarp();
+    return r;
+}
 static inline int si_g3_warp_max(int v) {
     si_g3_emu_warp->xchg[si_g3_emu_lane] = v;
     si_g3_syncwarp();
@@ -88,7 +98,7 @@ static inline int si_g3_warp_max(int v) {
 #else
 // ------------------------------------------------------------------ device
 #define SI_G3_DEV __device__ __forceinline__
-#define SI_G3_GLOBAL __global__ __launch_bounds__(128)
+#define SI_G3_GLOBAL(mb) __global__ __launch_bounds__(128, mb)
 #define SI_G3_KERNEL_PROLOGUE              \
     extern __shared__ double g3_smem[];    \
     const int g3_lane = threadIdx.x & 31, g3_warp = threadIdx.x >> 5;
@@ -97,6 +107,14 @@ __device__ __forceinline__ long long si_g3_next_group(int* counter, int lane) {
     int v = 0;
     if (lane == 0) v = atomicAdd(counter, 1);
     return (long long)__shfl_sync(0xffffffffu, v, 0);
+}
+__device__ __forceinline__ long long si_g3_fetch_group(int* counter, int lane) {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(counter, 1);
+    return (long long)v;
+}
+__device__ __forceinline__ long long si_g3_bcast_group(long long v) {
+    return (long long)__shfl_sync(0xffffffffu, (int)v, 0);
 }
 __device__ __forceinline__ int si_g3_warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 #endif

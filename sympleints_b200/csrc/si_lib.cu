@@ -764,7 +764,12 @@ struct Fan {
         return SI_OK;
     }
     int stream(cudaStream_t* s) {
-        int i = next++ % SI_NSTREAMS;
+        static int nstreams = -1;
+        if (nstreams < 0) {
+            const char* e = getenv("SI_NSTREAMS");
+            nstreams = e ? std::max(1, std::min(SI_NSTREAMS, atoi(e))) : SI_NSTREAMS;
+        }
+        int i = next++ % nstreams;
         if (!used[i]) {
             SI_CUDA(cudaStreamWaitEvent(c->streams[i], c->ev_fork, 0));
             used[i] = true;
@@ -888,6 +893,14 @@ static bool g3_disabled() {
     }
     return v == 1;
 }
+static bool g3_profile() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SI_G3_PROFILE");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 static void g3_fill_args(G3Args& ga, si_context* c, const BasisDev& orb, const BasisDev& aux, const SiPairItem* pairs,
                          const double* ppair, int npairs, const int* auxlist, int naux_c, int col_begin, const OutDesc& od, int* counter,
                          int tpw) {
@@ -979,6 +992,10 @@ int si_int3c2e(si_context* c, const si_basis* corb, const si_basis* caux, int sb
         if (rc) return rc;
         auto sp = span[job.Lc];
         cudaStream_t s;
+        // launches that fill the GPU on their own run back to back on one stream (concurrent residency
+        // of kernels with different shared-memory carve-outs costs more than their tails); small ones fan out
+        const bool big = (long long)job.pc->n * sp.second >= (long long)c->sm_count * 64;
+        if (big) fan.next = 0;
         rc = fan.stream(&s);
         if (rc) return rc;
         int* counter = c->d_counters + (c->next_counter++ % SI_NCOUNTERS);
@@ -993,7 +1010,21 @@ int si_int3c2e(si_context* c, const si_basis* corb, const si_basis* caux, int sb
                 g_last_error = "generated class does not fit into shared memory";
                 return SI_ERR_INTERNAL;
             }
-            if (g3_launch(g3[1], g3[0], ga, grid, block, smem, s)) return SI_ERR_INTERNAL;
+            if (g3_profile()) {
+                cudaEvent_t e0, e1;
+                cudaEventCreate(&e0);
+                cudaEventCreate(&e1);
+                cudaDeviceSynchronize();
+                cudaEventRecord(e0, s);
+                if (g3_launch(g3[1], g3[0], ga, grid, block, smem, s)) return SI_ERR_INTERNAL;
+                cudaEventRecord(e1, s);
+                cudaEventSynchronize(e1);
+                float ms = 0;
+                cudaEventElapsedTime(&ms, e0, e1);
+                fprintf(stderr, "G3PROF %d%d%d %.4f\n", job.pc->La, job.pc->Lb, job.Lc, ms);
+                cudaEventDestroy(e0);
+                cudaEventDestroy(e1);
+            } else if (g3_launch(g3[1], g3[0], ga, grid, block, smem, s)) return SI_ERR_INTERNAL;
         } else {
             size_t smem = 0;
             int nw = pick_warps(c, p->dev, 4, &smem);

@@ -8,7 +8,9 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_longlong, c_size_t, c_v
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libsympleints_b200.so"
+import os
+
+LIB_PATH = Path(os.environ.get("SYMPLEINTS_B200_LIB", PKG / "lib" / "libsympleints_b200.so"))
 
 KEYS = {"ovlp": 0, "kin": 1, "dpm": 2, "qpm": 3, "dqpm": 4, "coul": 5, "2c2e": 6, "3c2e_sph": 7, "3c2e": 7}
 NCOMP = {"ovlp": 1, "kin": 1, "dpm": 3, "qpm": 6, "dqpm": 3, "coul": 1, "2c2e": 1, "3c2e_sph": 1, "3c2e": 1}
