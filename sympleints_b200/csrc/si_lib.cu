@@ -346,14 +346,18 @@ struct si_basis {
         int n = 0;
         SiPairItem* d_items = nullptr;
     };
-    // precomputed primitive-pair data (9 doubles each) for coef / coef_pgto
-    double* d_ppair[2] = {nullptr, nullptr};
-    std::vector<PairClass> pair_classes;
-    // aux shells by angular momentum
-    struct AuxClass {
-        int Lc;
-        std::vector<int> shells;
+    // A set of shell pairs (i, j), i0 <= i < i1, j <= i, sorted into (La >= Lb) classes, with the
+    // precomputed primitive-pair data (9 doubles each) for coef / coef_pgto.
+    struct PairSet {
+        std::vector<PairClass> classes;
+        double* d_ppair[2] = {nullptr, nullptr};
+        long long rows = 0;   // packed rows covered by the set
+        int i0 = 0, i1 = 0;
     };
+    PairSet full;
+    std::vector<PairSet*> row_chunks;   // cached chunking of the host-buffer 3c2e path
+    long long row_chunk_bytes = 0;
+    int row_chunk_ncol = 0;
     bool pairs_built = false;
 };
 
@@ -639,6 +643,7 @@ int si_basis_create(si_context* c, int nshell, const int* L, const int* nprim, c
     return SI_OK;
 }
 
+static void free_pair_set(si_basis::PairSet* ps);
 int si_basis_destroy(si_basis* b) {
     if (!b) return SI_ERR_ARG;
     cudaSetDevice(b->ctx->device);
@@ -651,9 +656,11 @@ int si_basis_destroy(si_basis* b) {
     cudaFree(b->d_exps);
     cudaFree(b->d_coef);
     cudaFree(b->d_coef_pgto);
-    for (auto& pc : b->pair_classes) cudaFree(pc.d_items);
-    cudaFree(b->d_ppair[0]);
-    cudaFree(b->d_ppair[1]);
+    free_pair_set(&b->full);
+    for (auto* ps : b->row_chunks) {
+        free_pair_set(ps);
+        delete ps;
+    }
     delete b;
     return SI_OK;
 }
@@ -662,13 +669,22 @@ int si_basis_nbf(const si_basis* b, int sph) { return b ? (sph ? b->nbf_sph : b-
 int si_basis_nshell(const si_basis* b) { return b ? b->nshell : -1; }
 long long si_basis_packed_rows(const si_basis* b) { return b ? b->packed_rows : -1; }
 
-// Host shell-batcher: sort the shell pairs i >= j into (La >= Lb) classes, most
-// expensive (most primitive pairs) first.
-static int build_pair_classes(si_basis* b) {
-    if (b->pairs_built) return SI_OK;
+static void free_pair_set(si_basis::PairSet* ps) {
+    for (auto& pc : ps->classes) cudaFree(pc.d_items);
+    ps->classes.clear();
+    cudaFree(ps->d_ppair[0]);
+    cudaFree(ps->d_ppair[1]);
+    ps->d_ppair[0] = ps->d_ppair[1] = nullptr;
+}
+
+// Host shell-batcher: sort the shell pairs (i, j), i0 <= i < i1, j <= i, into (La >= Lb) classes, most
+// expensive (most primitive pairs) first, and precompute the primitive-pair quantities.
+static int build_pair_set(si_basis* b, int i0, int i1, si_basis::PairSet* ps) {
     std::map<std::pair<int, int>, std::vector<SiPairItem>> cls;
     long long prow = 0;
-    for (int i = 0; i < b->nshell; ++i)
+    ps->i0 = i0;
+    ps->i1 = i1;
+    for (int i = i0; i < i1; ++i)
         for (int j = 0; j <= i; ++j) {
             SiPairItem it;
             memset(&it, 0, sizeof(it));
@@ -685,7 +701,7 @@ static int build_pair_classes(si_basis* b) {
             prow += (long long)si_nsph(b->L[i]) * si_nsph(b->L[j]);
             cls[{b->L[it.sa], b->L[it.sb]}].push_back(it);
         }
-    // primitive-pair data, shared by all classes (offset per shell pair)
+    ps->rows = prow;
     {
         size_t npp = 0;
         for (auto& kv : cls)
@@ -717,8 +733,8 @@ static int build_pair_classes(si_basis* b) {
                             q[8] = std::exp(-mu * r2) * co[b->poff[it.sa] + i] * co[b->poff[it.sb] + j];
                         }
                 }
-            SI_CUDA(cudaMalloc((void**)&b->d_ppair[variant], std::max<size_t>(pp.size() * sizeof(double), 8)));
-            SI_CUDA(cudaMemcpy(b->d_ppair[variant], pp.data(), pp.size() * sizeof(double), cudaMemcpyHostToDevice));
+            SI_CUDA(cudaMalloc((void**)&ps->d_ppair[variant], std::max<size_t>(pp.size() * sizeof(double), 8)));
+            SI_CUDA(cudaMemcpy(ps->d_ppair[variant], pp.data(), pp.size() * sizeof(double), cudaMemcpyHostToDevice));
         }
     }
     for (auto& kv : cls) {
@@ -732,8 +748,15 @@ static int build_pair_classes(si_basis* b) {
         pc.n = (int)v.size();
         SI_CUDA(cudaMalloc((void**)&pc.d_items, v.size() * sizeof(SiPairItem)));
         SI_CUDA(cudaMemcpy(pc.d_items, v.data(), v.size() * sizeof(SiPairItem), cudaMemcpyHostToDevice));
-        b->pair_classes.push_back(pc);
+        ps->classes.push_back(pc);
     }
+    return SI_OK;
+}
+
+static int build_pair_classes(si_basis* b) {
+    if (b->pairs_built) return SI_OK;
+    int rc = build_pair_set(b, 0, b->nshell, &b->full);
+    if (rc) return rc;
     b->pairs_built = true;
     return SI_OK;
 }
@@ -822,7 +845,7 @@ static int run_two_index(si_context* c, const si_basis* cb, int key, int sph, in
     Fan fan{c, user};
     rc = fan.begin();
     if (rc) return rc;
-    for (auto& pc : b->pair_classes) {
+    for (auto& pc : b->full.classes) {
         DevProgram* p;
         rc = get_program(c, key, pc.La, pc.Lb, 0, sph, normalize, &p);
         if (rc) return rc;
@@ -928,8 +951,16 @@ static bool g3_config(const si_context* c, const int* g3, long long ngroups, int
     return true;
 }
 
+static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* caux, int sb, int se, int normalize,
+                        int layout, const si_basis::PairSet* pset, double* out_dev, size_t out_len, void* stream);
+
 int si_int3c2e(si_context* c, const si_basis* corb, const si_basis* caux, int sb, int se, int normalize, int layout,
                double* out_dev, size_t out_len, void* stream) {
+    return int3c2e_impl(c, corb, caux, sb, se, normalize, layout, nullptr, out_dev, out_len, stream);
+}
+
+static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* caux, int sb, int se, int normalize,
+                        int layout, const si_basis::PairSet* pset, double* out_dev, size_t out_len, void* stream) {
     if (!c || !corb || !caux || !out_dev) return SI_ERR_ARG;
     si_basis* orb = const_cast<si_basis*>(corb);
     const si_basis* aux = caux;
@@ -941,7 +972,9 @@ int si_int3c2e(si_context* c, const si_basis* corb, const si_basis* caux, int sb
     const int col_begin = aux->foff_sph[sb];
     const int col_end = (se == aux->nshell) ? aux->nbf_sph : aux->foff_sph[se];
     const long long naux_local = col_end - col_begin;
-    const long long rows = (layout == SI_LAYOUT_FULL) ? (long long)orb->nbf_sph * orb->nbf_sph : orb->packed_rows;
+    if (!pset) pset = &orb->full;
+    if (pset != &orb->full && layout != SI_LAYOUT_PACKED) return SI_ERR_ARG;
+    const long long rows = (layout == SI_LAYOUT_FULL) ? (long long)orb->nbf_sph * orb->nbf_sph : pset->rows;
     if ((unsigned long long)(rows * naux_local) > out_len) {
         g_last_error = "output buffer too small";
         return SI_ERR_ARG;
@@ -977,7 +1010,7 @@ int si_int3c2e(si_context* c, const si_basis* corb, const si_basis* caux, int sb
         double cost;
     };
     std::vector<Job> jobs;
-    for (auto& pc : orb->pair_classes)
+    for (auto& pc : pset->classes)
         for (auto& kv : span) {
             DevProgram* p;
             rc = get_program(c, SI_3C2E, pc.La, pc.Lb, kv.first, 1, normalize, &p);
@@ -1002,7 +1035,7 @@ int si_int3c2e(si_context* c, const si_basis* corb, const si_basis* caux, int sb
         const int* g3 = g3_find(job.pc->La, job.pc->Lb, job.Lc);
         if (g3 && normalize != SI_NORM_NONE && !g3_disabled()) {
             G3Args ga;
-            g3_fill_args(ga, c, od_orb, od_aux, job.pc->d_items, orb->d_ppair[normalize == SI_NORM_PGTO ? 1 : 0], job.pc->n, d_list + sp.first, sp.second, col_begin,
+            g3_fill_args(ga, c, od_orb, od_aux, job.pc->d_items, pset->d_ppair[normalize == SI_NORM_PGTO ? 1 : 0], job.pc->n, d_list + sp.first, sp.second, col_begin,
                          od, counter, g3[3]);
             int grid, block;
             size_t smem;
@@ -1082,14 +1115,19 @@ int si_int2c2e_h(si_context* c, const si_basis* b, int sph, int normalize, doubl
     size_t nbf = sph ? b->nbf_sph : b->nbf_cart;
     return run_host(c, nbf * nbf, out, [&](double* d) { return si_int2c2e(c, b, sph, normalize, d, nullptr); });
 }
-// Host-buffer 3c2e: the aux-shell range is cut into chunks; each chunk is computed into one of two
-// device staging buffers and copied to its column range of the host tensor with cudaMemcpy2DAsync on
-// a copy stream while the next chunk computes (the host buffer should be pinned for full overlap).
-int si_int3c2e_h(si_context* c, const si_basis* orb, const si_basis* aux, int sb, int se, int normalize, int layout,
+// Host-buffer 3c2e.  The tensor is produced chunk by chunk into two device staging buffers; while chunk
+// k+1 computes, chunk k is copied to the caller's host buffer on a copy stream (pin the host buffer for
+// full overlap).  PACKED layout: chunks are ranges of the first shell index, i.e. contiguous row blocks
+// of the host tensor -> one contiguous cudaMemcpyAsync each.  FULL layout: chunks are aux-shell ranges
+// (column blocks, cudaMemcpy2DAsync).
+int si_int3c2e_h(si_context* c, const si_basis* corb, const si_basis* aux, int sb, int se, int normalize, int layout,
                  double* out, size_t out_len) {
-    if (!c || !orb || !aux || !out) return SI_ERR_ARG;
+    if (!c || !corb || !aux || !out) return SI_ERR_ARG;
     if (sb < 0 || se > aux->nshell || sb >= se) return SI_ERR_ARG;
+    si_basis* orb = const_cast<si_basis*>(corb);
     SI_CUDA(cudaSetDevice(c->device));
+    int rc = build_pair_classes(orb);
+    if (rc) return rc;
     const long long rows = (layout == SI_LAYOUT_FULL) ? (long long)orb->nbf_sph * orb->nbf_sph : orb->packed_rows;
     const int col_begin = aux->foff_sph[sb];
     const int col_end = (se == aux->nshell) ? aux->nbf_sph : aux->foff_sph[se];
@@ -1098,50 +1136,99 @@ int si_int3c2e_h(si_context* c, const si_basis* orb, const si_basis* aux, int sb
         g_last_error = "output buffer too small";
         return SI_ERR_ARG;
     }
-    // chunk boundaries: ~equal numbers of columns, at most 1 GiB of staging per buffer
-    const long long max_cols = std::max<long long>(1, (1ll << 30) / (rows * 8));
-    const long long want = std::max<long long>(1, std::min<long long>(max_cols, (ncol + 7) / 8));
-    std::vector<int> cuts;
-    cuts.push_back(sb);
-    long long acc = 0;
-    for (int s = sb; s < se; ++s) {
-        acc += si_nsph(aux->L[s]);
-        if (acc >= want && s + 1 < se) {
-            cuts.push_back(s + 1);
-            acc = 0;
-        }
-    }
-    cuts.push_back(se);
-    long long maxc = 0;
-    for (size_t k = 0; k + 1 < cuts.size(); ++k) {
-        int e = cuts[k + 1];
-        long long cc = ((e == aux->nshell) ? aux->nbf_sph : aux->foff_sph[e]) - aux->foff_sph[cuts[k]];
-        maxc = std::max(maxc, cc);
-    }
+    long long stage_bytes = 1ll << 31;   // 2 GiB per staging buffer (SI_STAGE_BYTES overrides; used by the tests)
+    if (const char* e = getenv("SI_STAGE_BYTES")) stage_bytes = std::max(1024ll, atoll(e));
     double* stage[2] = {nullptr, nullptr};
     cudaStream_t s_comp, s_copy;
     cudaEvent_t ev_done[2], ev_free[2];
     SI_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
     SI_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
-        SI_CUDA(cudaMalloc((void**)&stage[i], (size_t)rows * maxc * sizeof(double)));
         SI_CUDA(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
         SI_CUDA(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
     }
-    int rc = SI_OK;
-    for (size_t k = 0; k + 1 < cuts.size() && rc == SI_OK; ++k) {
-        const int b = (int)(k & 1);
-        const int cs = cuts[k], ce = cuts[k + 1];
-        const long long c0 = aux->foff_sph[cs] - col_begin;
-        const long long cc = ((ce == aux->nshell) ? aux->nbf_sph : aux->foff_sph[ce]) - aux->foff_sph[cs];
-        if (k >= 2) SI_CUDA(cudaStreamWaitEvent(s_comp, ev_free[b], 0));
-        rc = si_int3c2e(c, orb, aux, cs, ce, normalize, layout, stage[b], (size_t)(rows * cc), (void*)s_comp);
-        if (rc != SI_OK) break;
-        SI_CUDA(cudaEventRecord(ev_done[b], s_comp));
-        SI_CUDA(cudaStreamWaitEvent(s_copy, ev_done[b], 0));
-        SI_CUDA(cudaMemcpy2DAsync(out + c0, (size_t)ncol * sizeof(double), stage[b], (size_t)cc * sizeof(double),
-                                  (size_t)cc * sizeof(double), (size_t)rows, cudaMemcpyDeviceToHost, s_copy));
-        SI_CUDA(cudaEventRecord(ev_free[b], s_copy));
+    size_t stage_elems = 0;
+    if (layout == SI_LAYOUT_PACKED) {
+        // (re)build the cached row chunking: consecutive first-shell ranges of <= stage_bytes each
+        if (orb->row_chunks.empty() || orb->row_chunk_ncol != (int)ncol || orb->row_chunk_bytes != stage_bytes) {
+            for (auto* ps : orb->row_chunks) {
+                free_pair_set(ps);
+                delete ps;
+            }
+            orb->row_chunks.clear();
+            const long long max_rows = std::max<long long>(1, stage_bytes / (ncol * 8));
+            int i0 = 0;
+            long long acc = 0;
+            for (int i = 0; i < orb->nshell; ++i) {
+                long long r = 0;
+                for (int j = 0; j <= i; ++j) r += (long long)si_nsph(orb->L[i]) * si_nsph(orb->L[j]);
+                if (acc > 0 && acc + r > max_rows) {
+                    auto* ps = new si_basis::PairSet;
+                    rc = build_pair_set(orb, i0, i, ps);
+                    if (rc) return rc;
+                    orb->row_chunks.push_back(ps);
+                    i0 = i;
+                    acc = 0;
+                }
+                acc += r;
+            }
+            auto* ps = new si_basis::PairSet;
+            rc = build_pair_set(orb, i0, orb->nshell, ps);
+            if (rc) return rc;
+            orb->row_chunks.push_back(ps);
+            orb->row_chunk_ncol = (int)ncol;
+            orb->row_chunk_bytes = stage_bytes;
+        }
+        for (auto* ps : orb->row_chunks) stage_elems = std::max(stage_elems, (size_t)(ps->rows * ncol));
+        for (int i = 0; i < 2; ++i) SI_CUDA(cudaMalloc((void**)&stage[i], stage_elems * sizeof(double)));
+        long long row0 = 0;
+        for (size_t k = 0; k < orb->row_chunks.size() && rc == SI_OK; ++k) {
+            const int b = (int)(k & 1);
+            auto* ps = orb->row_chunks[k];
+            if (k >= 2) SI_CUDA(cudaStreamWaitEvent(s_comp, ev_free[b], 0));
+            rc = int3c2e_impl(c, orb, aux, sb, se, normalize, layout, ps, stage[b], (size_t)(ps->rows * ncol), (void*)s_comp);
+            if (rc != SI_OK) break;
+            SI_CUDA(cudaEventRecord(ev_done[b], s_comp));
+            SI_CUDA(cudaStreamWaitEvent(s_copy, ev_done[b], 0));
+            SI_CUDA(cudaMemcpyAsync(out + row0 * ncol, stage[b], (size_t)(ps->rows * ncol) * sizeof(double),
+                                    cudaMemcpyDeviceToHost, s_copy));
+            SI_CUDA(cudaEventRecord(ev_free[b], s_copy));
+            row0 += ps->rows;
+        }
+    } else {
+        const long long max_cols = std::max<long long>(1, stage_bytes / (rows * 8));
+        const long long want = std::max<long long>(1, std::min<long long>(max_cols, (ncol + 3) / 4));
+        std::vector<int> cuts;
+        cuts.push_back(sb);
+        long long acc = 0;
+        for (int s = sb; s < se; ++s) {
+            acc += si_nsph(aux->L[s]);
+            if (acc >= want && s + 1 < se) {
+                cuts.push_back(s + 1);
+                acc = 0;
+            }
+        }
+        cuts.push_back(se);
+        long long maxc = 0;
+        for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+            int e = cuts[k + 1];
+            maxc = std::max<long long>(maxc, ((e == aux->nshell) ? aux->nbf_sph : aux->foff_sph[e]) - aux->foff_sph[cuts[k]]);
+        }
+        for (int i = 0; i < 2; ++i) SI_CUDA(cudaMalloc((void**)&stage[i], (size_t)rows * maxc * sizeof(double)));
+        for (size_t k = 0; k + 1 < cuts.size() && rc == SI_OK; ++k) {
+            const int b = (int)(k & 1);
+            const int cs = cuts[k], ce = cuts[k + 1];
+            const long long c0 = aux->foff_sph[cs] - col_begin;
+            const long long cc = ((ce == aux->nshell) ? aux->nbf_sph : aux->foff_sph[ce]) - aux->foff_sph[cs];
+            if (k >= 2) SI_CUDA(cudaStreamWaitEvent(s_comp, ev_free[b], 0));
+            rc = si_int3c2e(c, orb, aux, cs, ce, normalize, layout, stage[b], (size_t)(rows * cc), (void*)s_comp);
+            if (rc != SI_OK) break;
+            SI_CUDA(cudaEventRecord(ev_done[b], s_comp));
+            SI_CUDA(cudaStreamWaitEvent(s_copy, ev_done[b], 0));
+            SI_CUDA(cudaMemcpy2DAsync(out + c0, (size_t)ncol * sizeof(double), stage[b], (size_t)cc * sizeof(double),
+                                      (size_t)cc * sizeof(double), (size_t)rows, cudaMemcpyDeviceToHost, s_copy));
+            SI_CUDA(cudaEventRecord(ev_free[b], s_copy));
+        }
     }
     cudaError_t e1 = cudaStreamSynchronize(s_comp);
     cudaError_t e2 = cudaStreamSynchronize(s_copy);
