@@ -332,7 +332,7 @@ def run_ours(args, rank, world, local_rank):
             pass
         tfl = work["flops"] / (ms_per_step * 1e-3) / 1e12 / world   # per GPU
         roofline = {
-            "bound": "fp64", "kernel": "k_3c2e (all launches of the step are this kernel, one per class, 8 streams)",
+            "bound": "fp64", "kernel": "g3_kernel_<La><Lb><Lc> (generated class-specialised 3c2e kernels; every launch of the step is one of the 90 classes, serialised on one stream)",
             "achieved": tfl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tfl / fp64_peak if fp64_peak else None,
             "traffic": None,
             "peak_source": "DFMA microbenchmark si_fp64_peak() measured in this run (FP64 is not in MEASURED_PEAKS.json)",
