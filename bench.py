@@ -240,6 +240,8 @@ def run_ours(args, rank, world, local_rank):
     from sympleints_b200.shells import shells_to_soa
 
     torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     shells, sites, aux = build_system(args.natoms)
@@ -320,7 +322,7 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": work["integrals"] / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(mywork["bytes"]), "steps": n_e2e, "s_per_step": float(dt.item()),
                "pinned_host_buffer": pinned,
-               "path": "si_basis_create (H2D) + si_int3c2e_h (chunked compute overlapped with cudaMemcpy2DAsync D2H)"}
+               "path": "si_basis_create (H2D) + si_int3c2e_h (row-chunked compute overlapped with contiguous cudaMemcpyAsync D2H)"}
         del host
 
     if rank == 0:
@@ -418,7 +420,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--other-keys", action="store_true", help="also time the 1e set, coul and 2c2e (N=1)")
-    ap.add_argument("--ref-per-class", type=int, default=2)
+    ap.add_argument("--ref-per-class", type=int, default=16)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -27,6 +27,7 @@ import os as _os
 
 # per-class tuning (lanes per tuple, min CTAs/SM for __launch_bounds__) found by scripts/tune_g3.py
 DEFAULT_MB = int(_os.environ.get("SI_G3_MB", "1"))
+SKIP = set(filter(None, _os.environ.get("SI_G3_SKIP", "").split(",")))   # ablation timing only
 _TUNE_FILE = _os.path.join(_os.path.dirname(__file__), "tuning.json")
 TUNING = {}
 if _os.path.exists(_TUNE_FILE) and not _os.environ.get("SI_G3_NO_TUNING"):
@@ -213,8 +214,8 @@ class ClassGen:
         # D-tree arrays per level 0..Lc-1 (non-leaf), flat index relative to off(amin(level))
         self.D_OFF = {}
         for lev in range(0, max(Lc, 1)):
-            self.D_OFF[lev] = o - off(self.amin(lev))   # address of flat index f is D_OFF[lev] + f
-            o += self.NA - off(self.amin(lev))
+            self.D_OFF[lev] = o          # full-size arrays: address of flat index f is D_OFF[lev] + f
+            o += self.NA
         prim_end = o
         # contracted phase: Z[m][a][jb] over the (dead) primitive temporaries
         if self.Lb == 0:
@@ -332,14 +333,17 @@ class ClassGen:
         nsl_v = {n: self.nslots(ncart(n)) for n in range(1, L + 1)}
         for n in range(1, L + 1):
             for s in range(nsl_v[n]):
-                E(f"int vm_{n}_{s}; {{ int k = q + EPT * {s}; vm_{n}_{s} = g3_vrr_{name}_{n}[k < {ncart(n)} ? k : 0]; }}")
+                E(f"const int kc_{n}_{s} = min(q + EPT * {s}, {ncart(n) - 1}); const int vm_{n}_{s} = g3_vrr_{name}_{n}[kc_{n}_{s}];")
         nsl_d = self.nslots(self.NA)
         if Lc > 0:
             for s in range(nsl_d):
-                E(f"int nx_{s}, ny_{s}, nz_{s}, ds_{s}; double dfx_{s}, dfy_{s}, dfz_{s}; {{ int f = q + EPT * {s}; if (f >= {self.NA}) f = {self.NA - 1}; "
-                  f"int v = g3_dd_{name}[f]; int w = g3_df_{name}[f]; ds_{s} = (v >> 24) & 0xF; "
+                E(f"int nx_{s}, ny_{s}, nz_{s}, ds_{s}; double dfx_{s}, dfy_{s}, dfz_{s}; const int fc_{s} = min(q + EPT * {s}, {self.NA - 1}); "
+                  f"{{ const int f = fc_{s}; int v = g3_dd_{name}[f]; int w = g3_df_{name}[f]; ds_{s} = (v >> 24) & 0xF; "
                   f"nx_{s} = f - (v & 0xFF); ny_{s} = f - ((v >> 8) & 0xFF); nz_{s} = f - ((v >> 16) & 0xFF); "
                   f"dfx_{s} = (double)(w & 0xF); dfy_{s} = (double)((w >> 4) & 0xF); dfz_{s} = (double)((w >> 8) & 0xF); }}")
+                # leaf targets: index into a Y row (clamped) and validity of this lane's element
+                E(f"const bool yv_{s} = (q + EPT * {s} >= {off(La)}) && (q + EPT * {s} < {self.NA}); "
+                  f"const int yc_{s} = min(max(q + EPT * {s}, {off(La)}), {self.NA - 1}) - {off(La)};")
         E("")
         # ---- work loop over tuple groups
         E("// the next group index is fetched one iteration ahead so that the atomic's round trip is hidden")
@@ -363,7 +367,7 @@ class ClassGen:
         E("Ax[d] = A.orb.cen[3 * it.sa + d]; Bx[d] = A.orb.cen[3 * it.sb + d]; Cx[d] = A.aux.cen[3 * sc + d]; AB[d] = Ax[d] - Bx[d];")
         self.close()
         E("const int Kc_max = si_g3_warp_max(Kc);")
-        E("bool first = true;")
+        E(f"for (int i_ = q; i_ < {self.nm * self.YS}; i_ += EPT) W[{self.Y_OFF} + i_] = 0.0;   // contraction accumulator")
         self.open("for (int ia = 0; ia < Ka; ++ia)")
         E("const double ax = A.orb.exps[pa0 + ia], da = A.orb.coef[pa0 + ia];")
         self.open("for (int ib = 0; ib < Kb; ++ib)")
@@ -379,17 +383,19 @@ class ClassGen:
         E("// tuples with fewer aux primitives repeat their last one with zero weight")
         E("const int ikk = ik < Kc ? ik : Kc - 1;")
         E("const double cx = A.aux.exps[pc0 + ikk], dc = ik < Kc ? A.aux.coef[pc0 + ikk] : 0.0;")
-        E("const double ocx = 1.0 / cx;")
+        E("const double ocx = A.aux_oexp[pc0 + ikk];   // 1/c, precomputed by the host")
         self._emit_primitive()
-        E("first = false;")
         self.close()  # ik
         self.close()  # ib
         self.close()  # ia
         self.sync()
-        if Lb > 0:
+        if Lb > 0 and "hrr" not in SKIP:
             self._emit_hrr_c2sb()
             self.sync()
-        self._emit_c2s_a_store()
+        if "c2sa" not in SKIP:
+            self._emit_c2s_a_store()
+        else:
+            E("if (valid && q == 0) A.od.out[0] = W[0];")
         E("grp_next = si_g3_bcast_group(grp_next);")
         self.sync()
         self.close()  # for(;;)
@@ -410,7 +416,8 @@ class ClassGen:
         E = self.emit
         vm_n = self.vrr_meta()
         E("const double pc_ = p + cx;")
-        E("const double rpc = 1.0 / pc_;")
+        E("const double rs_ = si_g3_rsqrt(pc_);   // 1/sqrt(p+c)")
+        E("const double rpc = rs_ * rs_;")
         E("const double rho = p * cx * rpc;")
         E("const double rho_p = cx * rpc;          // rho / p")
         E("double PC[3]; double r2pc = 0.0;")
@@ -419,7 +426,7 @@ class ClassGen:
         self.close()
         E("const double T = rho * r2pc;")
         E("// 2 pi^2.5 / (sqrt(p+c) p c) * K_ab * d_c ;  1/sqrt(p+c) = sqrt(p+c) / (p+c)")
-        E("const double pref = 2.0 * SI_PI_25 * (sqrt(pc_) * rpc) * oop * ocx * Kab * dc;")
+        E("const double pref = 2.0 * SI_PI_25 * rs_ * oop * ocx * Kab * dc;")
         E("const double oo2p = 0.5 * oop, c2 = -0.5 * oop * rho_p;")
         E("const double beta = 0.5 * rpc;      // (rho/c)/(2p)")
         E("const double binv = 2.0 * pc_;")
@@ -440,40 +447,44 @@ class ClassGen:
         # Boys base values: V(0, jn, 0) = pref * F_{Lc+jn}(T)
         nb = L + 1
         self.open(f"for (int j = q; j < {nb}; j += EPT)")
-        E(f"W[{self.V_OFF[(0, 0)]} + j] = pref * si_boys(A.boys, {Lc} + j, T);")
+        if "boys" in SKIP:
+            E(f"W[{self.V_OFF[(0, 0)]} + j] = pref * (T + j);")
+        else:
+            E(f"W[{self.V_OFF[(0, 0)]} + j] = pref * si_boys_fast(A.boys, {Lc} + j, T);")
         self.close()
         # note: V(0,jn,0) are contiguous since ncart(0)=1
         for jn in range(nb):
             assert self.V_OFF[(0, jn)] == self.V_OFF[(0, 0)] + jn
         self.sync()
         # ---- VRR shells
-        for n in range(1, L + 1):
+        for n in range(1, (0 if "vrr" in SKIP else L) + 1):
             nc = ncart(n)
             njn = L - n + 1
-            for s in range(self.nslots(nc)):
-                partial = (s + 1) * EPT > nc
-                if partial:
-                    self.open(f"if (q + EPT * {s} < {nc})")
-                else:
-                    self.open("")
-                E(f"const int m_ = vm_{n}_{s}; const int d_ = m_ & 3; const int k1 = (m_ >> 8) & 0xFF; const int k2 = (m_ >> 16) & 0xFF;")
-                E(f"const double pa_ = W[{self.S_PA} + d_], cp_ = W[{self.S_CPC} + d_];")
-                if n >= 2:
-                    E("const double fc_ = (double)((m_ >> 2) & 0xF); const double f1 = fc_ * oo2p, f2 = fc_ * c2;")
-                E(f"const int k_ = q + EPT * {s};")
-                E(f"double u0 = W[{self.V_OFF[(n - 1, 0)]} + k1], u1;")
-                if n >= 2:
-                    E(f"double w0 = W[{self.V_OFF[(n - 2, 0)]} + k2], w1;")
-                for jn in range(njn):
-                    E(f"u1 = W[{self.V_OFF[(n - 1, jn + 1)]} + k1];")
+            # Shared-memory loads and stores of one stage touch disjoint arrays, but the compiler cannot
+            # know that (one array, per-lane indices) and would serialise LDS behind every STS.  So each
+            # stage is emitted as: all loads, all arithmetic, all stores.
+            self.open("")
+            nsl_n = self.nslots(nc)
+            for s in range(nsl_n):
+                # branch-free: lanes beyond the shell recompute (and re-store) its last component
+                E(f"const int m{s}_ = vm_{n}_{s}; const int d{s}_ = m{s}_ & 3; const int k1_{s} = (m{s}_ >> 8) & 0xFF; const int k2_{s} = (m{s}_ >> 16) & 0xFF;")
+                E(f"const double pa{s}_ = W[{self.S_PA} + d{s}_], cp{s}_ = W[{self.S_CPC} + d{s}_];")
+                for jn in range(njn + 1):
+                    E(f"const double u{s}_{jn} = W[{self.V_OFF[(n - 1, jn)]} + k1_{s}];")
                     if n >= 2:
-                        E(f"w1 = W[{self.V_OFF[(n - 2, jn + 1)]} + k2];")
-                        E(f"W[{self.V_OFF[(n, jn)]} + k_] = fma(f2, w1, fma(f1, w0, fma(pa_, u0, cp_ * u1)));")
-                        E("w0 = w1;")
+                        E(f"const double w{s}_{jn} = W[{self.V_OFF[(n - 2, jn)]} + k2_{s}];")
+            for s in range(nsl_n):
+                if n >= 2:
+                    E(f"const double fc{s}_ = (double)((m{s}_ >> 2) & 0xF); const double f1_{s} = fc{s}_ * oo2p, f2_{s} = fc{s}_ * c2;")
+                for jn in range(njn):
+                    if n >= 2:
+                        E(f"const double v{s}_{jn} = fma(f2_{s}, w{s}_{jn + 1}, fma(f1_{s}, w{s}_{jn}, fma(pa{s}_, u{s}_{jn}, cp{s}_ * u{s}_{jn + 1})));")
                     else:
-                        E(f"W[{self.V_OFF[(n, jn)]} + k_] = fma(pa_, u0, cp_ * u1);")
-                    E("u0 = u1;")
-                self.close()
+                        E(f"const double v{s}_{jn} = fma(pa{s}_, u{s}_{jn}, cp{s}_ * u{s}_{jn + 1});")
+            for s in range(nsl_n):
+                for jn in range(njn):
+                    E(f"W[{self.V_OFF[(n, jn)]} + kc_{n}_{s}] = v{s}_{jn};")
+            self.close()
             self.sync()
         # ---- D-tree
         if Lc == 0:
@@ -482,32 +493,37 @@ class ClassGen:
                 nc = ncart(n)
                 for s in range(self.nslots(nc)):
                     partial = (s + 1) * EPT > nc
-                    self.open(f"if (q + EPT * {s} < {nc})" if partial else "")
+                    self.open("")
                     ya = self.Y_OFF + off(n) - off(La)
-                    E(f"const int k_ = q + EPT * {s}; const double v_ = W[{self.V_OFF[(n, 0)]} + k_];")
-                    E(f"if (first) W[{ya} + k_] = v_; else W[{ya} + k_] += v_;")
+                    kk = f"kc_{n}_{s}" if n >= 1 else "0"
+                    E(f"const int k_ = {kk}; const double v_ = W[{ya} + k_] + W[{self.V_OFF[(n, 0)]} + k_];")
+                    E((f"if (q + EPT * {s} < {nc}) " if partial else "") + f"W[{ya} + k_] = v_;")
                     self.close()
             return
+        if "dtree" in SKIP:
+            return
         # root: h[f] = V(n, 0, k) * binv^n for shells amin(0)..L, stored at D_OFF[0] + f
-        E("{ double bq = 1.0;")
-        self.ind += 1
+        self.open("")
+        E("double bq = 1.0;")
+        idx = 0
+        stores = []
         for n in range(0, L + 1):
-            if n >= self.amin(0):
-                nc = ncart(n)
-                for s in range(self.nslots(nc)):
-                    partial = (s + 1) * EPT > nc
-                    cond = f"if (q + EPT * {s} < {nc}) " if partial else ""
-                    E(f"{cond}W[{self.D_OFF[0] + off(n)} + q + EPT * {s}] = W[{self.V_OFF[(n, 0)]} + q + EPT * {s}] * bq;")
+            for s in range(self.nslots(ncart(n))):
+                kk = f"kc_{n}_{s}" if n >= 1 else "0"
+                E(f"const double g{idx}_ = W[{self.V_OFF[(n, 0)]} + {kk}] * bq;")
+                stores.append(f"W[{self.D_OFF[0] + off(n)} + {kk}] = g{idx}_;")
+                idx += 1
             E("bq *= binv;")
-        self.ind -= 1
-        E("}")
+        for st in stores:
+            E(st)
+        self.close()
         self.sync()
         # DFS over monomials; direction sequences non-decreasing (x.., y.., z..)
         nsl = self.nslots(self.NA)
         # per-slot: own root values + beta powers for the leaves
         for s in range(nsl):
             lo = off(self.amin(0))
-            E(f"double r0_{s} = 0.0; {{ const int f = q + EPT * {s}; if (f >= {lo} && f < {self.NA}) r0_{s} = W[{self.D_OFF[0]} + f]; }}")
+            E(f"const double r0_{s} = W[{self.D_OFF[0]} + fc_{s}];")
         for s in range(nsl):
             E(f"const double bp_{s} = W[{self.S_BPOW} + ds_{s}];")
         al = ["alx", "aly", "alz"]
@@ -526,39 +542,38 @@ class ClassGen:
                 lo2 = off(self.amin(lev2))
                 self.open("")
                 E(f"// node {tuple(c2)} <- {tuple(c)} (+1_{'xyz'[d]})")
+                leaf_updates = []
+                act = []
                 for s in range(nsl):
                     smin, smax = s * EPT, s * EPT + EPT - 1
                     if smax < lo2 or smin >= self.NA:
                         if not leaf:
-                            E(f"double r{lev2}_{s} = 0.0;")
+                            E(f"const double r{lev2}_{s} = 0.0;")
                         continue
-                    full = smin >= lo2 and smax < self.NA
-                    E("{" if leaf else f"double r{lev2}_{s} = 0.0; {{")
-                    self.ind += 1
-                    E(f"const int f = q + EPT * {s};")
-                    if not full:
-                        self.open(f"if (f >= {lo2} && f < {self.NA})")
-                    E(f"const double nb_ = W[{self.D_OFF[level]} + {'nx ny nz'.split()[d]}_{s}];")
-                    E(f"const double v_ = fma({dfn[d]}_{s}, nb_, {al[d]} * r{level}_{s});")
+                    act.append(s)
+                for s in act:
+                    E(f"const double nb{lev2}_{s} = W[{self.D_OFF[level]} + {'nx ny nz'.split()[d]}_{s}];")
+                for s in act:
+                    E(f"const double r{lev2}_{s} = fma({dfn[d]}_{s}, nb{lev2}_{s}, {al[d]} * r{level}_{s});")
+                for s in act:
                     if leaf:
                         ci = cidx(c2)
-                        E(f"const double t_ = bp_{s} * v_;")
+                        E(f"const double t{lev2}_{s} = bp_{s} * r{lev2}_{s};")
                         for m in range(self.nm):
                             if Mc[m][ci] == 0.0:
                                 continue
                             coef = lit(Mc[m][ci] * fc[ci])
-                            ya = self.Y_OFF + m * self.YS - off(La)
-                            if (m, s) not in seen:
-                                seen.add((m, s))
-                                E(f"if (first) W[{ya} + f] = {coef} * t_; else W[{ya} + f] = fma({coef}, t_, W[{ya} + f]);")
-                            else:
-                                E(f"W[{ya} + f] = fma({coef}, t_, W[{ya} + f]);")
+                            ya = self.Y_OFF + m * self.YS
+                            leaf_updates.append((s, f"W[{ya} + yc_{s}]", coef, f"t{lev2}_{s}"))
                     else:
-                        E(f"r{lev2}_{s} = v_; W[{self.D_OFF[lev2]} + f] = v_;")
-                    if not full:
-                        self.close()
-                    self.ind -= 1
-                    E("}")
+                        E(f"W[{self.D_OFF[lev2]} + fc_{s}] = r{lev2}_{s};")
+                # read-modify-write of the spherical accumulators: all loads, all FMAs, then predicated stores
+                for k_, (s, addr, coef, t) in enumerate(leaf_updates):
+                    E(f"const double yo{k_} = {addr};")
+                for k_, (s, addr, coef, t) in enumerate(leaf_updates):
+                    E(f"const double yn{k_} = fma({coef}, {t}, yo{k_});")
+                for k_, (s, addr, coef, t) in enumerate(leaf_updates):
+                    E(f"if (yv_{s}) {addr} = yn{k_};")
                 if not leaf:
                     self.sync()
                     rec(c2, lev2, d)
@@ -642,7 +657,8 @@ class ClassGen:
                 nk = sum(k)
                 const = off(La + nk) - off(La) + ik * (ik + 1) // 2 + k[2]
                 E(f"const double {ent[2]} = W[yb{ik} + {const}];")
-            else:
+        for ent in order:
+            if ent[0] != "in":
                 _, key, name, n1, n2, d = ent
                 E(f"const double {name} = fma(AB[{d}], {n2}, {n1});")
         # C2S(b)
@@ -653,7 +669,9 @@ class ClassGen:
                 if Mb[jb][j] == 0.0:
                     continue
                 expr = f"{lit(coef)} * {targets[j]}" if expr is None else f"fma({lit(coef)}, {targets[j]}, {expr})"
-            E(f"W[{self.Z_OFF} + m * {self.ZS} + ai * {nsb} + {jb}] = {expr};")
+            E(f"const double zb{jb} = {expr};")
+        for jb in range(nsb):
+            E(f"W[{self.Z_OFF} + m * {self.ZS} + ai * {nsb} + {jb}] = zb{jb};")
         self.close()
 
     # ---- C2S(a) + global store --------------------------------------------------------------

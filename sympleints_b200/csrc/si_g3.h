@@ -42,6 +42,7 @@ struct G3Args {
     const SiPairItem* pairs;
     const double* ppair;  // 9 doubles per primitive pair: p, 1/p, P[3], PA[3], exp(-mu AB^2) da db
     int npairs;
+    const double* aux_oexp;  // 1/exponent of every aux primitive
     const int* auxlist;   // aux shells of this class (same Lc)
     int naux_c;
     int col_begin;
@@ -54,8 +55,11 @@ struct G3Args {
 
 #if defined(SI_G3_HOST_EMU)
 // ------------------------------------------------------------------ host warp emulation
+#include <algorithm>
 #include <atomic>
 #include <barrier>
+using std::max;
+using std::min;
 struct SiG3EmuWarp {
     std::barrier<>* bar;
     volatile long long xchg[32];
@@ -70,6 +74,7 @@ extern thread_local int si_g3_emu_lane;
     double* g3_smem = si_g3_emu_smem;                           \
     const int g3_lane = si_g3_emu_lane, g3_warp = 0;
 static inline void si_g3_syncwarp() { si_g3_emu_warp->bar->arrive_and_wait(); }
+static inline double si_g3_rsqrt(double x) { return 1.0 / sqrt(x); }
 static inline long long si_g3_next_group(int* counter, int lane) {
     if (lane == 0) si_g3_emu_warp->xchg[0] = __atomic_fetch_add(counter, 1, __ATOMIC_SEQ_CST);
     si_g3_syncwarp();
@@ -103,6 +108,7 @@ static inline int si_g3_warp_max(int v) {
     extern __shared__ double g3_smem[];    \
     const int g3_lane = threadIdx.x & 31, g3_warp = threadIdx.x >> 5;
 __device__ __forceinline__ void si_g3_syncwarp() { __syncwarp(); }
+__device__ __forceinline__ double si_g3_rsqrt(double x) { return rsqrt(x); }
 __device__ __forceinline__ long long si_g3_next_group(int* counter, int lane) {
     int v = 0;
     if (lane == 0) v = atomicAdd(counter, 1);

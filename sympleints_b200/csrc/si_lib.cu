@@ -335,11 +335,11 @@ struct si_basis {
     si_context* ctx = nullptr;
     int nshell = 0;
     std::vector<int> L, nprim, poff, foff_sph, foff_cart;
-    std::vector<double> cen, exps, coef, coef_pgto;
+    std::vector<double> cen, exps, coef, coef_pgto, oexp;
     int nbf_sph = 0, nbf_cart = 0, lmax = 0;
     long long packed_rows = 0;
     int *d_L = nullptr, *d_nprim = nullptr, *d_poff = nullptr, *d_foff_sph = nullptr, *d_foff_cart = nullptr;
-    double *d_cen = nullptr, *d_exps = nullptr, *d_coef = nullptr, *d_coef_pgto = nullptr;
+    double *d_cen = nullptr, *d_exps = nullptr, *d_coef = nullptr, *d_coef_pgto = nullptr, *d_oexp = nullptr;
     // shell-pair classes (La >= Lb), cost-sorted, on the device
     struct PairClass {
         int La, Lb;
@@ -639,6 +639,9 @@ int si_basis_create(si_context* c, int nshell, const int* L, const int* nprim, c
     SI_CUDA(upload(b->exps, &b->d_exps));
     SI_CUDA(upload(b->coef, &b->d_coef));
     SI_CUDA(upload(b->coef_pgto, &b->d_coef_pgto));
+    b->oexp.resize(np);
+    for (int i = 0; i < np; ++i) b->oexp[i] = 1.0 / b->exps[i];
+    SI_CUDA(upload(b->oexp, &b->d_oexp));
     *out = b;
     return SI_OK;
 }
@@ -656,6 +659,7 @@ int si_basis_destroy(si_basis* b) {
     cudaFree(b->d_exps);
     cudaFree(b->d_coef);
     cudaFree(b->d_coef_pgto);
+    cudaFree(b->d_oexp);
     free_pair_set(&b->full);
     for (auto* ps : b->row_chunks) {
         free_pair_set(ps);
@@ -924,11 +928,13 @@ static bool g3_profile() {
     }
     return v == 1;
 }
-static void g3_fill_args(G3Args& ga, si_context* c, const BasisDev& orb, const BasisDev& aux, const SiPairItem* pairs,
+static void g3_fill_args(G3Args& ga, si_context* c, const BasisDev& orb, const BasisDev& aux, const double* aux_oexp,
+                         const SiPairItem* pairs,
                          const double* ppair, int npairs, const int* auxlist, int naux_c, int col_begin, const OutDesc& od, int* counter,
                          int tpw) {
     ga.orb = orb;
     ga.aux = aux;
+    ga.aux_oexp = aux_oexp;
     ga.pairs = pairs;
     ga.ppair = ppair;
     ga.npairs = npairs;
@@ -1035,7 +1041,7 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
         const int* g3 = g3_find(job.pc->La, job.pc->Lb, job.Lc);
         if (g3 && normalize != SI_NORM_NONE && !g3_disabled()) {
             G3Args ga;
-            g3_fill_args(ga, c, od_orb, od_aux, job.pc->d_items, pset->d_ppair[normalize == SI_NORM_PGTO ? 1 : 0], job.pc->n, d_list + sp.first, sp.second, col_begin,
+            g3_fill_args(ga, c, od_orb, od_aux, aux->d_oexp, job.pc->d_items, pset->d_ppair[normalize == SI_NORM_PGTO ? 1 : 0], job.pc->n, d_list + sp.first, sp.second, col_begin,
                          od, counter, g3[3]);
             int grid, block;
             size_t smem;
@@ -1401,7 +1407,7 @@ int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int n
                 if (e == cudaSuccess) e = cudaMemcpy(d_pp, pp.data(), pp.size() * sizeof(double), cudaMemcpyHostToDevice);
                 item.ppoff = 0;
                 if (e == cudaSuccess) e = cudaMemcpy(d_item, &item, sizeof(item), cudaMemcpyHostToDevice);
-                g3_fill_args(ga, c, bd, ad, d_item, d_pp, 1, d_list1, 1, 0, od, d_counter, g3[3]);
+                g3_fill_args(ga, c, bd, ad, xb->d_oexp, d_item, d_pp, 1, d_list1, 1, 0, od, d_counter, g3[3]);
                 int grid, block;
                 size_t sm2;
                 if (e == cudaSuccess && g3_config(c, g3, ga.ngroups, &grid, &block, &sm2))

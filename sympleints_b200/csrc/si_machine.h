@@ -191,6 +191,35 @@ SI_HD double si_boys(const SiBoys& B, int n, double x) {
 #endif
 }
 
+// Same algorithm, cheaper evaluation for the generated kernels: Horner form of the 6-term Taylor sum and
+// x^(-n-1/2) = sqrt(1/x) (1/x)^n by binary exponentiation instead of pow() (differences ~1e-16 relative).
+SI_HD double si_boys_fast(const SiBoys& B, int n, double x) {
+    if (x < 30.0) {
+        if (x == 0.0) return B.table[n * B.ncols];
+        const int ind0 = (int)(x * 10.0);
+        const double mdx = ind0 * 0.1 - x;
+        const double* t = B.table + n * B.ncols + ind0;
+        const int nc = B.ncols;
+        double r = t[5 * nc] * (1.0 / 120.0);
+        r = fma(r, mdx, t[4 * nc] * (1.0 / 24.0));
+        r = fma(r, mdx, t[3 * nc] * (1.0 / 6.0));
+        r = fma(r, mdx, t[2 * nc] * 0.5);
+        r = fma(r, mdx, t[nc]);
+        r = fma(r, mdx, t[0]);
+        return r;
+    }
+    const double inv = 1.0 / x;
+    double acc = sqrt(inv), b = inv;
+    int e = n;
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+        if (e & 1) acc *= b;
+        b *= b;
+        e >>= 1;
+    }
+    return B.xlarge_pref[n] * acc;
+}
+
 // ---- dynamic scalar table fill ----------------------------------------------
 // v[12]: four 3-vectors (V0..V3); kb[5]: bases of the k-multiples; s0: single.
 SI_HD void si_fill_scalars(double* S, const double* v, const double* kb, double s0, int lane,

@@ -44,8 +44,11 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
         afoff[i] = i * (2 * Lc + 1);
         alist[i] = i;
     }
+    std::vector<double> oexp(np);
+    for (int i = 0; i < np; ++i) oexp[i] = 1.0 / cx[i];
     G3Args args;
     memset(&args, 0, sizeof(args));
+    args.aux_oexp = oexp.data();
     args.orb = BasisDev{oL, onp, opoff, ofoff, ocen.data(), oex.data(), oco.data()};
     args.aux = BasisDev{aL.data(), anp.data(), apoff.data(), afoff.data(), C, cx, dc};
     SiPairItem item;
