@@ -56,7 +56,10 @@ def _compile_obj(src, obj, verbose):
 
 def build_library(force=False, verbose=False, jobs=None):
     gen = generate_sources()
-    deps = SOURCES + HEADERS + [CSRC / "si_g3.h", PKG / "codegen" / "gen3c2e.py"]
+    deps = SOURCES + HEADERS + [CSRC / "si_g3.h", PKG / "codegen" / "gen3c2e.py", GENDIR / "g3_table.inc"] + gen
+    tj = PKG / "codegen" / "tuning.json"
+    if tj.exists():
+        deps.append(tj)
     if not force and LIB.exists() and all(p.stat().st_mtime <= LIB.stat().st_mtime for p in deps):
         return LIB
     LIBDIR.mkdir(exist_ok=True)
