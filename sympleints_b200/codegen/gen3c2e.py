@@ -27,6 +27,7 @@ import os as _os
 
 # per-class tuning (lanes per tuple, min CTAs/SM for __launch_bounds__) found by scripts/tune_g3.py
 DEFAULT_MB = int(_os.environ.get("SI_G3_MB", "1"))
+YREG_MAX = int(_os.environ.get("SI_G3_YREG", "36"))   # max doubles of register accumulators per lane
 SKIP = set(filter(None, _os.environ.get("SI_G3_SKIP", "").split(",")))   # ablation timing only
 _TUNE_FILE = _os.path.join(_os.path.dirname(__file__), "tuning.json")
 TUNING = {}
@@ -180,6 +181,11 @@ class ClassGen:
         self.EPT = ept
         self.TPW = 32 // ept
         self.name = f"{La}{Lb}{Lc}"
+        # spherical accumulators Y[m][a'] in registers (per lane: nm x target slots) when they fit
+        tslots = [s for s in range((self.NA + ept - 1) // ept) if (s + 1) * ept - 1 >= off(La) and s * ept < self.NA]
+        self.tslots = tslots
+        ymax = tune.get("yreg", YREG_MAX)
+        self.YREG = Lc > 0 and self.nm * len(tslots) <= ymax
         self.lines = []
         self.ind = 1
         self._layout()
@@ -367,7 +373,11 @@ class ClassGen:
         E("Ax[d] = A.orb.cen[3 * it.sa + d]; Bx[d] = A.orb.cen[3 * it.sb + d]; Cx[d] = A.aux.cen[3 * sc + d]; AB[d] = Ax[d] - Bx[d];")
         self.close()
         E("const int Kc_max = si_g3_warp_max(Kc);")
-        E(f"for (int i_ = q; i_ < {self.nm * self.YS}; i_ += EPT) W[{self.Y_OFF} + i_] = 0.0;   // contraction accumulator")
+        if self.YREG:
+            for m in range(self.nm):
+                E("double " + ", ".join(f"ya_{m}_{s} = 0.0" for s in self.tslots) + ";   // contraction accumulators (registers)")
+        else:
+            E(f"for (int i_ = q; i_ < {self.nm * self.YS}; i_ += EPT) W[{self.Y_OFF} + i_] = 0.0;   // contraction accumulator")
         self.open("for (int ia = 0; ia < Ka; ++ia)")
         E("const double ax = A.orb.exps[pa0 + ia], da = A.orb.coef[pa0 + ia];")
         self.open("for (int ib = 0; ib < Kb; ++ib)")
@@ -388,6 +398,11 @@ class ClassGen:
         self.close()  # ik
         self.close()  # ib
         self.close()  # ia
+        if self.YREG:
+            self.sync("last primitive's readers of the overlaid arrays are done")
+            for m in range(self.nm):
+                for s in self.tslots:
+                    E(f"if (yv_{s}) W[{self.Y_OFF + m * self.YS} + yc_{s}] = ya_{m}_{s};")
         self.sync()
         if Lb > 0 and "hrr" not in SKIP:
             self._emit_hrr_c2sb()
@@ -564,7 +579,10 @@ class ClassGen:
                                 continue
                             coef = lit(Mc[m][ci] * fc[ci])
                             ya = self.Y_OFF + m * self.YS
-                            leaf_updates.append((s, f"W[{ya} + yc_{s}]", coef, f"t{lev2}_{s}"))
+                            if self.YREG:
+                                E(f"ya_{m}_{s} = fma({coef}, t{lev2}_{s}, ya_{m}_{s});")
+                            else:
+                                leaf_updates.append((s, f"W[{ya} + yc_{s}]", coef, f"t{lev2}_{s}"))
                     else:
                         E(f"W[{self.D_OFF[lev2]} + fc_{s}] = r{lev2}_{s};")
                 # read-modify-write of the spherical accumulators: all loads, all FMAs, then predicated stores
