@@ -242,6 +242,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug_%h_%p.log")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     shells, sites, aux = build_system(args.natoms)
@@ -250,6 +251,8 @@ def run_ours(args, rank, world, local_rank):
     costs = workmodel.aux_shell_costs(shells, aux)
     ranges = sdist.partition_aux_shells(costs, world)
     my = ranges[rank]
+    if args.shard_of > 1:   # debugging aid: time rank 0's shard of an N-way partition on one GPU
+        my = sdist.partition_aux_shells(costs, args.shard_of)[0]
     work = workmodel.tensor_3c2e_work(shells, aux)
     mywork = workmodel.tensor_3c2e_work(shells, aux, my)
     ncol = eng.aux_cols(ab, *my)
@@ -421,6 +424,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--other-keys", action="store_true", help="also time the 1e set, coul and 2c2e (N=1)")
     ap.add_argument("--ref-per-class", type=int, default=16)
+    ap.add_argument("--shard-of", type=int, default=1, help="debug: run only rank 0's shard of an N-way partition")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

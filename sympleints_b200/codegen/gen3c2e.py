@@ -770,13 +770,14 @@ def write_sources(outdir, lmax=4, lauxmax=5, nparts=15):
             src.append(gens[c].generate())
         # launcher for this part
         src.append("#if !defined(SI_G3_HOST_EMU)")
-        src.append(f"int g3_launch_part_{pi}(int id, const G3Args& A, int grid, int block, size_t smem, cudaStream_t s) {{")
+        src.append(f"int g3_launch_part_{pi}(int id, const G3Args& A, int grid, int block, size_t smem, int max_smem, cudaStream_t s) {{")
         src.append("    switch (id) {")
         for c in cl:
             g = gens[c]
             cid = c[0] * 100 + c[1] * 10 + c[2]
-            src.append(f"        case {cid}: cudaFuncSetAttribute(g3_kernel_{g.name}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);"
-                       f" g3_kernel_{g.name}<<<grid, block, smem, s>>>(A); return 0;")
+            src.append(f"        case {cid}: {{ static bool once = false; if (!once) {{ cudaFuncSetAttribute(g3_kernel_{g.name}, "
+                       f"cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); once = true; }} "
+                       f"g3_kernel_{g.name}<<<grid, block, smem, s>>>(A); return 0; }}")
             table.append((cid, pi, g.EPT, g.TPW, g.WSZ))
         src.append("        default: return 1;")
         src.append("    }")
@@ -795,12 +796,12 @@ def write_sources(outdir, lmax=4, lauxmax=5, nparts=15):
     lines.append("};")
     for pi, cl in enumerate(parts):
         if cl:
-            lines.append(f"int g3_launch_part_{pi}(int id, const G3Args& A, int grid, int block, size_t smem, cudaStream_t s);")
-    lines.append("static int g3_launch(int part, int id, const G3Args& A, int grid, int block, size_t smem, cudaStream_t s) {")
+            lines.append(f"int g3_launch_part_{pi}(int id, const G3Args& A, int grid, int block, size_t smem, int max_smem, cudaStream_t s);")
+    lines.append("static int g3_launch(int part, int id, const G3Args& A, int grid, int block, size_t smem, int max_smem, cudaStream_t s) {")
     lines.append("    switch (part) {")
     for pi, cl in enumerate(parts):
         if cl:
-            lines.append(f"        case {pi}: return g3_launch_part_{pi}(id, A, grid, block, smem, s);")
+            lines.append(f"        case {pi}: return g3_launch_part_{pi}(id, A, grid, block, smem, max_smem, s);")
     lines.append("        default: return 1;")
     lines.append("    }")
     lines.append("}")

@@ -359,6 +359,13 @@ struct si_basis {
     long long row_chunk_bytes = 0;
     int row_chunk_ncol = 0;
     bool pairs_built = false;
+    // cached device lists of the aux shells of a range, grouped by angular momentum (3c2e)
+    struct AuxRange {
+        int sb, se;
+        int* d_list = nullptr;
+        std::map<int, std::pair<int, int>> span;
+    };
+    mutable std::vector<AuxRange> aux_ranges;
 };
 
 const char* si_strerror(int status) {
@@ -660,6 +667,7 @@ int si_basis_destroy(si_basis* b) {
     cudaFree(b->d_coef);
     cudaFree(b->d_coef_pgto);
     cudaFree(b->d_oexp);
+    for (auto& r : b->aux_ranges) cudaFree(r.d_list);
     free_pair_set(&b->full);
     for (auto* ps : b->row_chunks) {
         free_pair_set(ps);
@@ -992,18 +1000,32 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
     od.nbf = orb->nbf_sph;
     od.mode = (layout == SI_LAYOUT_FULL) ? STORE_3C_FULL : STORE_3C_PACKED;
     cudaStream_t user = (cudaStream_t)stream;
-    // aux shells of the range by angular momentum
-    std::map<int, std::vector<int>> by_l;
-    for (int s = sb; s < se; ++s) by_l[aux->L[s]].push_back(s);
-    std::vector<int> flat;
-    std::map<int, std::pair<int, int>> span;
-    for (auto& kv : by_l) {
-        span[kv.first] = {(int)flat.size(), (int)kv.second.size()};
-        flat.insert(flat.end(), kv.second.begin(), kv.second.end());
+    // aux shells of the range by angular momentum (device list cached per range)
+    const si_basis::AuxRange* ar = nullptr;
+    for (auto& r : aux->aux_ranges)
+        if (r.sb == sb && r.se == se) ar = &r;
+    if (!ar) {
+        std::map<int, std::vector<int>> by_l;
+        for (int s = sb; s < se; ++s) by_l[aux->L[s]].push_back(s);
+        std::vector<int> flat;
+        si_basis::AuxRange r;
+        r.sb = sb;
+        r.se = se;
+        for (auto& kv : by_l) {
+            r.span[kv.first] = {(int)flat.size(), (int)kv.second.size()};
+            flat.insert(flat.end(), kv.second.begin(), kv.second.end());
+        }
+        SI_CUDA(cudaMalloc((void**)&r.d_list, flat.size() * sizeof(int)));
+        SI_CUDA(cudaMemcpy(r.d_list, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (aux->aux_ranges.size() >= 64) {
+            cudaFree(aux->aux_ranges.front().d_list);
+            aux->aux_ranges.erase(aux->aux_ranges.begin());
+        }
+        aux->aux_ranges.push_back(r);
+        ar = &aux->aux_ranges.back();
     }
-    int* d_list = nullptr;
-    SI_CUDA(cudaMallocAsync((void**)&d_list, flat.size() * sizeof(int), user));
-    SI_CUDA(cudaMemcpyAsync(d_list, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, user));
+    const std::map<int, std::pair<int, int>>& span = ar->span;
+    int* d_list = ar->d_list;
     BasisDev od_orb = basis_dev(orb, 1, normalize);
     BasisDev od_aux = basis_dev(aux, 1, normalize);
     Fan fan{c, user};
@@ -1029,7 +1051,7 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
         DevProgram* p;
         rc = get_program(c, SI_3C2E, job.pc->La, job.pc->Lb, job.Lc, 1, normalize, &p);
         if (rc) return rc;
-        auto sp = span[job.Lc];
+        auto sp = span.at(job.Lc);
         cudaStream_t s;
         // launches that fill the GPU on their own run back to back on one stream (concurrent residency
         // of kernels with different shared-memory carve-outs costs more than their tails); small ones fan out
@@ -1055,7 +1077,7 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
                 cudaEventCreate(&e1);
                 cudaDeviceSynchronize();
                 cudaEventRecord(e0, s);
-                if (g3_launch(g3[1], g3[0], ga, grid, block, smem, s)) return SI_ERR_INTERNAL;
+                if (g3_launch(g3[1], g3[0], ga, grid, block, smem, c->max_smem, s)) return SI_ERR_INTERNAL;
                 cudaEventRecord(e1, s);
                 cudaEventSynchronize(e1);
                 float ms = 0;
@@ -1063,7 +1085,7 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
                 fprintf(stderr, "G3PROF %d%d%d %.4f\n", job.pc->La, job.pc->Lb, job.Lc, ms);
                 cudaEventDestroy(e0);
                 cudaEventDestroy(e1);
-            } else if (g3_launch(g3[1], g3[0], ga, grid, block, smem, s)) return SI_ERR_INTERNAL;
+            } else if (g3_launch(g3[1], g3[0], ga, grid, block, smem, c->max_smem, s)) return SI_ERR_INTERNAL;
         } else {
             size_t smem = 0;
             int nw = pick_warps(c, p->dev, 4, &smem);
@@ -1080,7 +1102,6 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
         SI_CUDA(cudaGetLastError());
     }
     rc = fan.end();
-    cudaFreeAsync(d_list, user);
     return rc;
 }
 
@@ -1411,7 +1432,7 @@ int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int n
                 int grid, block;
                 size_t sm2;
                 if (e == cudaSuccess && g3_config(c, g3, ga.ngroups, &grid, &block, &sm2))
-                    g3_launch(g3[1], g3[0], ga, 1, 32, (size_t)g3[4] * g3[3] * sizeof(double), 0);
+                    g3_launch(g3[1], g3[0], ga, 1, 32, (size_t)g3[4] * g3[3] * sizeof(double), c->max_smem, 0);
                 if (e == cudaSuccess) e = cudaDeviceSynchronize();
                 cudaFree(d_list1);
                 cudaFree(d_pp);
