@@ -448,17 +448,30 @@ class ClassGen:
         E("const double rho_c = p * rpc;       // rho / c")
         E("const double alx = rho_c * PC[0], aly = rho_c * PC[1], alz = rho_c * PC[2];")
         E("(void)alx; (void)aly; (void)alz; (void)beta; (void)binv;")
-        self.sync("previous primitive's readers are done")
+        # No barrier is needed before overwriting the scalar area and the Boys values: their last readers
+        # (VRR shells, start of the aux recurrence) are separated from here by at least one barrier of the
+        # previous primitive whenever several lanes share a tuple (EPT > 1 implies La + Lb >= 1).
+        # Exception: with Lc == 1 the aux recurrence has no barrier of its own, so the beta powers read at
+        # its start could still be in use.
+        if L == 0 or Lc == 1:
+            self.sync("previous primitive's readers are done")
         # scalars to shared memory (lane q==0 of the tuple)
         self.open("if (q == 0)")
         for d in range(3):
             E(f"W[{self.S_PA + d}] = PA[{d}]; W[{self.S_CPC + d}] = -rho_p * PC[{d}];")
-        if Lc > 0:
+        if Lc > 0 and EPT <= 2:
             E("{ double bp = 1.0;")
             for n in range(L + 1):
                 E(f"  W[{self.S_BPOW + n}] = bp; bp *= beta;")
             E("}")
         self.close()
+        if Lc > 0 and EPT > 2:
+            # beta^j, one power per lane (binary powering) instead of a serial chain on one lane
+            self.open(f"for (int j = q; j < {L + 1}; j += EPT)")
+            E("double bp = 1.0, bb = beta; int e_ = j;")
+            E("for (int it_ = 0; it_ < 4; ++it_) { if (e_ & 1) bp *= bb; bb *= bb; e_ >>= 1; }")
+            E(f"W[{self.S_BPOW} + j] = bp;")
+            self.close()
         # Boys base values: V(0, jn, 0) = pref * F_{Lc+jn}(T)
         nb = L + 1
         self.open(f"for (int j = q; j < {nb}; j += EPT)")
