@@ -194,7 +194,20 @@ class ClassGen:
     def amin(self, level):
         return max(0, self.La - (self.Lc - level))
 
-    def _layout(self):
+    def _layout(self, ypad=None, zpad=None):
+        """Shared-memory layout.  The strides of the Y rows and Z slabs are padded such that the
+        strided accesses of the contracted phase (lanes differ in (component, m)) spread over the
+        banks; the paddings are found by simulating the half-warp bank pattern (_conflicts)."""
+        if ypad is None:
+            best = None
+            for yp in range(0, 8):
+                for zp in (range(0, 8) if self.Lb > 0 else [0]):
+                    self._layout(yp, zp)
+                    c = (self._conflicts(), self.WSZ)
+                    if best is None or c < best[0]:
+                        best = (c, yp, zp)
+            self._layout(best[1], best[2])
+            return
         L, Lc = self.L, self.Lc
         o = 0
         self.S_OFF = o          # scalars: PA[3], CPC[3], BPOW[L+1]
@@ -204,8 +217,8 @@ class ClassGen:
             o += 1
         # Y[m][a'] persistent over primitives: the leaves of the aux recurrence are folded straight
         # into the spherical components (C2S on c), so no Cartesian [a0|c] block is ever stored
-        self.YS = self.n_ap | 1                    # odd stride between m rows of Y
-        self.ZS = (self.nca * self.nsb) | 1        # odd stride between m slabs of Z
+        self.YS = self.n_ap + ypad                 # stride between m rows of Y
+        self.ZS = self.nca * self.nsb + zpad       # stride between m slabs of Z
         if self.Lb == 0:
             self.ZS = self.YS
         self.Y_OFF = o
@@ -234,6 +247,60 @@ class ClassGen:
         if w % 2 == 0:
             w += 1               # odd stride: conflict-free when several tuples share a warp
         self.WSZ = w
+
+    def _conflicts(self):
+        """Shared-memory wavefronts of the strided stages (HRR gather, Z store, C2S(a) loads) for the
+        current layout: per LDS.64/STS.64 each half-warp costs as many wavefronts as the largest number
+        of distinct addresses that fall into one 8-byte bank (16 banks)."""
+        EPT, TPW = self.EPT, self.TPW
+        nm, nca, nsb, La, Lb = self.nm, self.nca, self.nsb, self.La, self.Lb
+
+        def cost(addrs):
+            tot = 0
+            for h in (addrs[:16], addrs[16:]):
+                banks = {}
+                for a in h:
+                    if a is None:
+                        continue
+                    banks.setdefault(a % 16, set()).add(a)
+                tot += max((len(v) for v in banks.values()), default=0)
+            return tot
+
+        total = 0
+        if Lb > 0:
+            nit = nca * nm
+            ks = [k for n in range(Lb + 1) for k in cart_order(n)]
+            for r in range((nit + EPT - 1) // EPT):
+                lanes = []
+                for lane in range(32):
+                    q, tl = lane % EPT, lane // EPT
+                    item = q + EPT * r
+                    if item >= nit:
+                        lanes.append(None)
+                        continue
+                    ai, m = divmod(item, nm)
+                    ia = 0
+                    while (ia + 1) * (ia + 2) // 2 <= ai:
+                        ia += 1
+                    lanes.append((tl, ai, m, ia))
+                for k in ks:
+                    ik = k[1] + k[2]
+                    const = off(La + sum(k)) - off(La) + ik * (ik + 1) // 2 + k[2]
+                    total += cost([None if t is None else t[0] * self.WSZ + self.Y_OFF + t[2] * self.YS + t[1] + t[3] * ik + const
+                                   for t in lanes])
+                for jb in range(nsb):
+                    total += cost([None if t is None else t[0] * self.WSZ + self.Z_OFF + t[2] * self.ZS + t[1] * nsb + jb
+                                   for t in lanes])
+        nit = nsb * nm
+        for r in range((nit + EPT - 1) // EPT):
+            lanes = []
+            for lane in range(32):
+                q, tl = lane % EPT, lane // EPT
+                item = q + EPT * r
+                lanes.append(None if item >= nit else (tl,) + divmod(item, nm))
+            for a in range(nca):
+                total += cost([None if t is None else t[0] * self.WSZ + self.Z_OFF + t[2] * self.ZS + a * nsb + t[1] for t in lanes])
+        return total
 
     # ---- emission helpers ---------------------------------------------------------------
     def emit(self, s=""):
