@@ -419,12 +419,16 @@ class ClassGen:
                   f"const int yc_{s} = min(max(q + EPT * {s}, {off(La)}), {self.NA - 1}) - {off(La)};")
         E("")
         # ---- work loop over tuple groups
-        E("// the next group index is fetched one iteration ahead so that the atomic's round trip is hidden")
-        E("long long grp_next = si_g3_next_group(A.counter, lane);")
+        E("// Work is handed out in chunks of A.chunk consecutive groups per atomic (one global counter would")
+        E("// otherwise serialise ~10^7 same-address atomics per step); the next chunk index is fetched one")
+        E("// chunk ahead so that the atomic's round trip is hidden.")
+        E("long long ch_next = si_g3_next_group(A.counter, lane);")
         self.open("for (;;)")
-        E("const long long grp = grp_next;")
-        E("if (grp >= A.ngroups) break;")
-        E("grp_next = si_g3_fetch_group(A.counter, lane);   // raw atomic result of lane 0, broadcast at the loop end")
+        E("const long long ch = ch_next;")
+        E("if (ch * A.chunk >= A.ngroups) break;")
+        E("ch_next = si_g3_fetch_group(A.counter, lane);   // raw atomic result of lane 0, broadcast at the chunk end")
+        E("const long long g_end = min((ch + 1) * (long long)A.chunk, A.ngroups);")
+        self.open("for (long long grp = ch * A.chunk; grp < g_end; ++grp)")
         E("// group -> (pair, first aux of the group); tuples beyond the run end recompute the last valid one")
         E("const int ip = (int)(grp / A.groups_per_pair);")
         E("const int gi = (int)(grp - (long long)ip * A.groups_per_pair);")
@@ -432,13 +436,11 @@ class ClassGen:
         E("const bool valid = ic < A.naux_c;")
         E("if (!valid) ic = A.naux_c - 1;")
         E("const SiPairItem it = A.pairs[ip];")
-        E("const int sc = A.auxlist[ic];")
-        E("const int Ka = A.orb.nprim[it.sa], Kb = A.orb.nprim[it.sb], Kc = A.aux.nprim[sc];")
-        E("const int pa0 = A.orb.poff[it.sa], pb0 = A.orb.poff[it.sb], pc0 = A.aux.poff[sc];")
-        E("double Ax[3], Bx[3], Cx[3], AB[3];")
-        self.open("for (int d = 0; d < 3; ++d)")
-        E("Ax[d] = A.orb.cen[3 * it.sa + d]; Bx[d] = A.orb.cen[3 * it.sb + d]; Cx[d] = A.aux.cen[3 * sc + d]; AB[d] = Ax[d] - Bx[d];")
-        self.close()
+        E("const SiAuxItem ai_ = A.auxitems[ic];")
+        E("const int sc = ai_.shell; (void)sc;")
+        E("const int Ka = it.Ka, Kb = it.Kb, Kc = ai_.Kc, pc0 = ai_.pc0;")
+        E("const double Cx[3] = {ai_.C[0], ai_.C[1], ai_.C[2]};")
+        E("const double AB[3] = {it.AB[0], it.AB[1], it.AB[2]};")
         E("const int Kc_max = si_g3_warp_max(Kc);")
         if self.YREG:
             for m in range(self.nm):
@@ -446,22 +448,22 @@ class ClassGen:
         else:
             E(f"for (int i_ = q; i_ < {self.nm * self.YS}; i_ += EPT) W[{self.Y_OFF} + i_] = 0.0;   // contraction accumulator")
         self.open("for (int ia = 0; ia < Ka; ++ia)")
-        E("const double ax = A.orb.exps[pa0 + ia], da = A.orb.coef[pa0 + ia];")
         self.open("for (int ib = 0; ib < Kb; ++ib)")
-        E("const double bx = A.orb.exps[pb0 + ib], db = A.orb.coef[pb0 + ib];")
         E("// primitive-pair data precomputed by the host shell-batcher: p, 1/p, P[3], PA[3], exp(-mu AB^2) da db")
         E("const double* pp = A.ppair + (size_t)(it.ppoff + ia * Kb + ib) * 9;")
         E("const double p = pp[0], oop = pp[1];")
         E("const double P[3] = {pp[2], pp[3], pp[4]};")
         E("const double PA[3] = {pp[5], pp[6], pp[7]};")
         E("const double Kab = pp[8];")
-        E("(void)ax; (void)bx; (void)da; (void)db;")
         self.open("for (int ik = 0; ik < Kc_max; ++ik)")
         E("// tuples with fewer aux primitives repeat their last one with zero weight")
         E("const int ikk = ik < Kc ? ik : Kc - 1;")
         E("const double cx = A.aux.exps[pc0 + ikk], dc = ik < Kc ? A.aux.coef[pc0 + ikk] : 0.0;")
         E("const double ocx = A.aux_oexp[pc0 + ikk];   // 1/c, precomputed by the host")
-        self._emit_primitive()
+        if "prim" in SKIP:      # ablation: keep only the loads of the primitive data
+            E("if (q == 0) W[0] = p + oop + P[0] + PA[0] + Kab + cx + dc + ocx;")
+        else:
+            self._emit_primitive()
         self.close()  # ik
         self.close()  # ib
         self.close()  # ia
@@ -478,8 +480,9 @@ class ClassGen:
             self._emit_c2s_a_store()
         else:
             E("if (valid && q == 0) A.od.out[0] = W[0];")
-        E("grp_next = si_g3_bcast_group(grp_next);")
         self.sync()
+        self.close()  # groups of the chunk
+        E("ch_next = si_g3_bcast_group(ch_next);")
         self.close()  # for(;;)
         self.close()  # function
         E("")
@@ -780,8 +783,8 @@ class ClassGen:
         Ma = cart2sph(La)
         fa = lmn_factors(La)
         nit = nsb * nm
-        E("const long long col = (long long)(A.aux.foff[sc] - A.col_begin);")
-        E("const int fa0 = A.orb.foff ? A.orb.foff[it.sa] : 0, fb0 = A.orb.foff ? A.orb.foff[it.sb] : 0;")
+        E("const long long col = (long long)(ai_.foff - A.col_begin);")
+        E("const int fa0 = it.fa0, fb0 = it.fb0;")
         self.open(f"for (int item = q; item < {nit}; item += EPT)")
         E(f"const int jb = item / {nm}, m = item - jb * {nm};")
         for a in range(nca):

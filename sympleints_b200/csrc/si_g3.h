@@ -20,11 +20,20 @@ struct BasisDev {
     const double* coef;
 };
 
-struct SiPairItem {
+struct SiPairItem {   // 64 bytes: everything the kernels need about a shell pair in ONE load
     int sa, sb;       // shell indices; L(sa) >= L(sb)
     int swapped;      // packed layout: 1 if sa is the column shell of the (i>=j) block
     int ppoff;        // first primitive pair of this shell pair in the precomputed pair-data array
     long long prow;   // first row of the pair block in the packed 3-index layout
+    int Ka, Kb;       // contraction lengths
+    int fa0, fb0;     // spherical function offsets of the two shells
+    double AB[3];     // A - B
+};
+
+struct SiAuxItem {    // 48 bytes: one auxiliary shell of the class being processed
+    int shell, Kc, pc0, foff;
+    double C[3];
+    double pad;
 };
 
 enum StoreMode { STORE_BLOCK = 0, STORE_MATRIX = 1, STORE_3C_FULL = 2, STORE_3C_PACKED = 3 };
@@ -44,10 +53,12 @@ struct G3Args {
     int npairs;
     const double* aux_oexp;  // 1/exponent of every aux primitive
     const int* auxlist;   // aux shells of this class (same Lc)
+    const SiAuxItem* auxitems;  // the same shells as packed records (generated kernels)
     int naux_c;
     int col_begin;
     int groups_per_pair;  // ceil(naux_c / tuples-per-warp)
     long long ngroups;    // npairs * groups_per_pair
+    int chunk;            // groups handed out per atomic
     OutDesc od;
     int* counter;
     SiBoys boys;

@@ -363,6 +363,7 @@ struct si_basis {
     struct AuxRange {
         int sb, se;
         int* d_list = nullptr;
+        SiAuxItem* d_items = nullptr;
         std::map<int, std::pair<int, int>> span;
     };
     mutable std::vector<AuxRange> aux_ranges;
@@ -667,7 +668,10 @@ int si_basis_destroy(si_basis* b) {
     cudaFree(b->d_coef);
     cudaFree(b->d_coef_pgto);
     cudaFree(b->d_oexp);
-    for (auto& r : b->aux_ranges) cudaFree(r.d_list);
+    for (auto& r : b->aux_ranges) {
+        cudaFree(r.d_list);
+        cudaFree(r.d_items);
+    }
     free_pair_set(&b->full);
     for (auto* ps : b->row_chunks) {
         free_pair_set(ps);
@@ -710,6 +714,11 @@ static int build_pair_set(si_basis* b, int i0, int i1, si_basis::PairSet* ps) {
                 it.swapped = 1;
             }
             it.prow = prow;
+            it.Ka = b->nprim[it.sa];
+            it.Kb = b->nprim[it.sb];
+            it.fa0 = b->foff_sph[it.sa];
+            it.fb0 = b->foff_sph[it.sb];
+            for (int d = 0; d < 3; ++d) it.AB[d] = b->cen[3 * it.sa + d] - b->cen[3 * it.sb + d];
             prow += (long long)si_nsph(b->L[i]) * si_nsph(b->L[j]);
             cls[{b->L[it.sa], b->L[it.sb]}].push_back(it);
         }
@@ -928,6 +937,14 @@ static bool g3_disabled() {
     }
     return v == 1;
 }
+static int g3_chunk() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SI_G3_CHUNK");
+        v = e ? std::max(1, atoi(e)) : 1;
+    }
+    return v;
+}
 static bool g3_profile() {
     static int v = -1;
     if (v < 0) {
@@ -938,8 +955,8 @@ static bool g3_profile() {
 }
 static void g3_fill_args(G3Args& ga, si_context* c, const BasisDev& orb, const BasisDev& aux, const double* aux_oexp,
                          const SiPairItem* pairs,
-                         const double* ppair, int npairs, const int* auxlist, int naux_c, int col_begin, const OutDesc& od, int* counter,
-                         int tpw) {
+                         const double* ppair, int npairs, const int* auxlist, const SiAuxItem* auxitems, int naux_c, int col_begin,
+                         const OutDesc& od, int* counter, int tpw) {
     ga.orb = orb;
     ga.aux = aux;
     ga.aux_oexp = aux_oexp;
@@ -947,10 +964,12 @@ static void g3_fill_args(G3Args& ga, si_context* c, const BasisDev& orb, const B
     ga.ppair = ppair;
     ga.npairs = npairs;
     ga.auxlist = auxlist;
+    ga.auxitems = auxitems;
     ga.naux_c = naux_c;
     ga.col_begin = col_begin;
     ga.groups_per_pair = (naux_c + tpw - 1) / tpw;
     ga.ngroups = (long long)npairs * ga.groups_per_pair;
+    ga.chunk = g3_chunk();
     ga.od = od;
     ga.counter = counter;
     ga.boys = c->boys_dev;
@@ -1017,8 +1036,21 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
         }
         SI_CUDA(cudaMalloc((void**)&r.d_list, flat.size() * sizeof(int)));
         SI_CUDA(cudaMemcpy(r.d_list, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+        std::vector<SiAuxItem> aitems(flat.size());
+        for (size_t i = 0; i < flat.size(); ++i) {
+            const int sh = flat[i];
+            memset(&aitems[i], 0, sizeof(SiAuxItem));
+            aitems[i].shell = sh;
+            aitems[i].Kc = aux->nprim[sh];
+            aitems[i].pc0 = aux->poff[sh];
+            aitems[i].foff = aux->foff_sph[sh];
+            for (int d = 0; d < 3; ++d) aitems[i].C[d] = aux->cen[3 * sh + d];
+        }
+        SI_CUDA(cudaMalloc((void**)&r.d_items, aitems.size() * sizeof(SiAuxItem)));
+        SI_CUDA(cudaMemcpy(r.d_items, aitems.data(), aitems.size() * sizeof(SiAuxItem), cudaMemcpyHostToDevice));
         if (aux->aux_ranges.size() >= 64) {
             cudaFree(aux->aux_ranges.front().d_list);
+            cudaFree(aux->aux_ranges.front().d_items);
             aux->aux_ranges.erase(aux->aux_ranges.begin());
         }
         aux->aux_ranges.push_back(r);
@@ -1026,6 +1058,7 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
     }
     const std::map<int, std::pair<int, int>>& span = ar->span;
     int* d_list = ar->d_list;
+    const SiAuxItem* d_aitems = ar->d_items;
     BasisDev od_orb = basis_dev(orb, 1, normalize);
     BasisDev od_aux = basis_dev(aux, 1, normalize);
     Fan fan{c, user};
@@ -1063,7 +1096,7 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
         const int* g3 = g3_find(job.pc->La, job.pc->Lb, job.Lc);
         if (g3 && normalize != SI_NORM_NONE && !g3_disabled()) {
             G3Args ga;
-            g3_fill_args(ga, c, od_orb, od_aux, aux->d_oexp, job.pc->d_items, pset->d_ppair[normalize == SI_NORM_PGTO ? 1 : 0], job.pc->n, d_list + sp.first, sp.second, col_begin,
+            g3_fill_args(ga, c, od_orb, od_aux, aux->d_oexp, job.pc->d_items, pset->d_ppair[normalize == SI_NORM_PGTO ? 1 : 0], job.pc->n, d_list + sp.first, d_aitems + sp.first, sp.second, col_begin,
                          od, counter, g3[3]);
             int grid, block;
             size_t smem;
@@ -1427,8 +1460,23 @@ int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int n
                 if (e == cudaSuccess) e = cudaMalloc((void**)&d_pp, pp.size() * sizeof(double));
                 if (e == cudaSuccess) e = cudaMemcpy(d_pp, pp.data(), pp.size() * sizeof(double), cudaMemcpyHostToDevice);
                 item.ppoff = 0;
+                item.Ka = nps[0];
+                item.Kb = nps[1];
+                item.fa0 = 0;
+                item.fb0 = 0;
+                for (int d = 0; d < 3; ++d) item.AB[d] = A_[d] - B_[d];
                 if (e == cudaSuccess) e = cudaMemcpy(d_item, &item, sizeof(item), cudaMemcpyHostToDevice);
-                g3_fill_args(ga, c, bd, ad, xb->d_oexp, d_item, d_pp, 1, d_list1, 1, 0, od, d_counter, g3[3]);
+                SiAuxItem aitem;
+                memset(&aitem, 0, sizeof(aitem));
+                aitem.shell = 0;
+                aitem.Kc = Kc;
+                aitem.pc0 = 0;
+                aitem.foff = 0;
+                for (int d = 0; d < 3; ++d) aitem.C[d] = C[d];
+                SiAuxItem* d_aitem = nullptr;
+                if (e == cudaSuccess) e = cudaMalloc((void**)&d_aitem, sizeof(aitem));
+                if (e == cudaSuccess) e = cudaMemcpy(d_aitem, &aitem, sizeof(aitem), cudaMemcpyHostToDevice);
+                g3_fill_args(ga, c, bd, ad, xb->d_oexp, d_item, d_pp, 1, d_list1, d_aitem, 1, 0, od, d_counter, g3[3]);
                 int grid, block;
                 size_t sm2;
                 if (e == cudaSuccess && g3_config(c, g3, ga.ngroups, &grid, &block, &sm2))
@@ -1436,6 +1484,7 @@ int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int n
                 if (e == cudaSuccess) e = cudaDeviceSynchronize();
                 cudaFree(d_list1);
                 cudaFree(d_pp);
+                cudaFree(d_aitem);
             } else {
                 k_3c2e<<<1, 32, smem>>>(P, c->boys_dev, bd, ad, d_item, 1, nullptr, 1, 0, od, d_counter);
             }

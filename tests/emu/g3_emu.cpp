@@ -70,6 +70,20 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
             q[8] = exp(-mu * r2) * da[i] * db[j];
         }
     item.ppoff = 0;
+    item.Ka = Ka;
+    item.Kb = Kb;
+    item.fa0 = 0;
+    item.fb0 = 2 * La + 1;
+    for (int d = 0; d < 3; ++d) item.AB[d] = A[d] - B[d];
+    std::vector<SiAuxItem> aitems(naux);
+    for (int i = 0; i < naux; ++i) {
+        aitems[i].shell = i;
+        aitems[i].Kc = Kc[i];
+        aitems[i].pc0 = apoff[i];
+        aitems[i].foff = afoff[i];
+        for (int d = 0; d < 3; ++d) aitems[i].C[d] = C[3 * i + d];
+    }
+    args.auxitems = aitems.data();
     args.ppair = pp.data();
     args.pairs = &item;
     args.npairs = 1;
@@ -78,6 +92,7 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
     args.col_begin = 0;
     args.groups_per_pair = (naux + cls->tpw - 1) / cls->tpw;
     args.ngroups = args.groups_per_pair;
+    args.chunk = 2;
     const int na = 2 * La + 1, nb = 2 * Lb + 1, nc = 2 * Lc + 1;
     // full layout of a 2-shell orbital basis: (nbf, nbf, naux*nc); we extract the (a, b) block afterwards
     const int nbf = na + nb;
