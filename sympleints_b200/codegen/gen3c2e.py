@@ -400,7 +400,7 @@ class ClassGen:
         self.ind = 1
         E(f"constexpr int EPT = {EPT}, TPW = {TPW}, WSZ = {self.WSZ};")
         E("const int q = lane % EPT, tl = lane / EPT;")
-        E("double* const W = wbase + tl * WSZ;")
+        E("SI_G3_WTYPE W = SI_G3_WINIT(wbase + tl * WSZ, WSZ);")
         E("(void)q;")
         # ---- per-lane metadata
         nsl_v = {n: self.nslots(ncart(n)) for n in range(1, L + 1)}

@@ -67,6 +67,8 @@ struct G3Args {
 #if defined(SI_G3_HOST_EMU)
 // ------------------------------------------------------------------ host warp emulation
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <atomic>
 #include <barrier>
 using std::max;
@@ -79,6 +81,20 @@ extern thread_local SiG3EmuWarp* si_g3_emu_warp;
 extern thread_local int si_g3_emu_lane;
 #define __device__
 #define SI_G3_DEV static inline
+// bounds-checked view of the tuple's shared-memory region (host emulation only)
+struct SiG3CheckedW {
+    double* p;
+    int n;
+    double& operator[](long long i) const {
+        if (i < 0 || i >= n) {
+            fprintf(stderr, "g3 emulation: shared-memory index %lld outside [0,%d)\n", i, n);
+            abort();
+        }
+        return p[i];
+    }
+};
+#define SI_G3_WTYPE const SiG3CheckedW
+#define SI_G3_WINIT(ptr, n) SiG3CheckedW{ptr, n}
 #define SI_G3_GLOBAL(mb) static inline
 #define SI_G3_KERNEL_PROLOGUE                                   \
     extern thread_local double* si_g3_emu_smem;                 \
@@ -114,6 +130,8 @@ static inline int si_g3_warp_max(int v) {
 #else
 // ------------------------------------------------------------------ device
 #define SI_G3_DEV __device__ __forceinline__
+#define SI_G3_WTYPE double* const
+#define SI_G3_WINIT(ptr, n) (ptr)
 #define SI_G3_GLOBAL(mb) __global__ __launch_bounds__(128, mb)
 #define SI_G3_KERNEL_PROLOGUE              \
     extern __shared__ double g3_smem[];    \

@@ -93,8 +93,9 @@ def emu_eval(key, La, Lb, Lc, shell_a, shell_b, shell_c=None, R=None, q=None, sp
 
 
 # ---- warp emulator of the GENERATED 3c2e kernels (tests/emu/g3_emu.cpp) ------------------------
-G3_EMU_CLASSES = [(0, 0, 0), (0, 0, 2), (1, 0, 1), (1, 1, 0), (1, 1, 2), (2, 0, 3), (2, 1, 2), (2, 2, 1),
-                  (3, 1, 4), (3, 3, 2), (4, 2, 5), (4, 4, 5)]
+# every (La >= Lb) pair with two aux momenta each + the extremes: 34 of the 90 classes
+G3_EMU_CLASSES = sorted({(a, b, c) for a in range(5) for b in range(a + 1) for c in ((a + b) % 6, (2 * a + b + 3) % 6)}
+                        | {(0, 0, 0), (0, 0, 5), (4, 4, 5), (4, 4, 0), (4, 0, 5), (2, 2, 1)})
 _G3 = None
 
 
