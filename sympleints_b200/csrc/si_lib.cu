@@ -1088,7 +1088,12 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
         cudaStream_t s;
         // launches that fill the GPU on their own run back to back on one stream (concurrent residency
         // of kernels with different shared-memory carve-outs costs more than their tails); small ones fan out
-        const bool big = (long long)job.pc->n * sp.second >= (long long)c->sm_count * 64;
+        static int force_fan = -1;
+        if (force_fan < 0) {
+            const char* e = getenv("SI_FORCE_FAN");
+            force_fan = (e && e[0] == '1') ? 1 : 0;
+        }
+        const bool big = !force_fan && (long long)job.pc->n * sp.second >= (long long)c->sm_count * 64;
         if (big) fan.next = 0;
         rc = fan.stream(&s);
         if (rc) return rc;
