@@ -817,7 +817,11 @@ def generate_file(classes):
 
 
 def all_classes(lmax=4, lauxmax=5):
-    return [(a, b, c) for a in range(lmax + 1) for b in range(a + 1) for c in range(lauxmax + 1)]
+    """The 3c2e classes (La >= Lb <= lmax, Lc <= lauxmax) plus (La, 0 | Lc) for lmax < La <= lauxmax: the
+    2c2e metric (a|b) is evaluated as (a s0 | b) with a unit s "function" of exponent 0 (p = a, P = A)."""
+    cl = [(a, b, c) for a in range(lmax + 1) for b in range(a + 1) for c in range(lauxmax + 1)]
+    cl += [(a, 0, c) for a in range(lmax + 1, lauxmax + 1) for c in range(lauxmax + 1)]
+    return cl
 
 
 def class_info(lmax=4, lauxmax=5):

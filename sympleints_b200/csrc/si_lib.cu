@@ -280,6 +280,13 @@ __global__ void __launch_bounds__(256) k_3c2e(SiProg P, SiBoys Bt, BasisDev orb,
     }
 }
 
+// copy the lower triangle of an n x n matrix into the upper one (exact symmetry, as intor_2c mirrors)
+__global__ void k_mirror_lower(double* m, long long n) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long i = blockIdx.y;
+    if (j < n && j > i) m[i * n + j] = m[j * n + i];
+}
+
 __global__ void k_boys_eval(SiBoys Bt, int n, const double* x, size_t nx, double* out) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < nx) out[i] = si_boys(Bt, n, x[i]);
@@ -367,6 +374,9 @@ struct si_basis {
         std::map<int, std::pair<int, int>> span;
     };
     mutable std::vector<AuxRange> aux_ranges;
+    // 2c2e through the generated 3c2e kernels: (a|b) = (a s0|b) with a unit s shell of exponent 0
+    mutable si_basis* twoc_orb = nullptr;     // copy of this basis + the s0 shell (last)
+    mutable PairSet* twoc_pairs = nullptr;    // pairs (shell j, s0)
 };
 
 const char* si_strerror(int status) {
@@ -668,6 +678,11 @@ int si_basis_destroy(si_basis* b) {
     cudaFree(b->d_coef);
     cudaFree(b->d_coef_pgto);
     cudaFree(b->d_oexp);
+    if (b->twoc_pairs) {
+        free_pair_set(b->twoc_pairs);
+        delete b->twoc_pairs;
+    }
+    if (b->twoc_orb) si_basis_destroy(b->twoc_orb);
     for (auto& r : b->aux_ranges) {
         cudaFree(r.d_list);
         cudaFree(r.d_items);
@@ -695,13 +710,14 @@ static void free_pair_set(si_basis::PairSet* ps) {
 
 // Host shell-batcher: sort the shell pairs (i, j), i0 <= i < i1, j <= i, into (La >= Lb) classes, most
 // expensive (most primitive pairs) first, and precompute the primitive-pair quantities.
-static int build_pair_set(si_basis* b, int i0, int i1, si_basis::PairSet* ps) {
+static int build_pair_set(si_basis* b, int i0, int i1, si_basis::PairSet* ps, bool skip_diagonal = false) {
     std::map<std::pair<int, int>, std::vector<SiPairItem>> cls;
     long long prow = 0;
     ps->i0 = i0;
     ps->i1 = i1;
     for (int i = i0; i < i1; ++i)
         for (int j = 0; j <= i; ++j) {
+            if (skip_diagonal && j == i) continue;
             SiPairItem it;
             memset(&it, 0, sizeof(it));
             if (b->L[i] >= b->L[j]) {
@@ -900,9 +916,48 @@ int si_int1e(si_context* c, const si_basis* b, int key, int sph, int normalize, 
     return run_two_index(c, b, key, sph, normalize, R, 0, nullptr, nullptr, out_dev, (cudaStream_t)stream);
 }
 
+static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* caux, int sb, int se, int normalize,
+                        int layout, const si_basis::PairSet* pset, double* out_dev, size_t out_len, void* stream);
+static bool g3_disabled();
+
 int si_int2c2e(si_context* c, const si_basis* b, int sph, int normalize, double* out_dev, void* stream) {
     if (!c || !b || !out_dev) return SI_ERR_ARG;
-    return run_two_index(c, b, SI_2C2E, sph, normalize, nullptr, 0, nullptr, nullptr, out_dev, (cudaStream_t)stream);
+    if (b->lmax > c->lauxmax) return SI_ERR_LMAX;
+    if (!sph || normalize == SI_NORM_NONE || g3_disabled())
+        return run_two_index(c, b, SI_2C2E, sph, normalize, nullptr, 0, nullptr, nullptr, out_dev, (cudaStream_t)stream);
+    // Spherical 2c2e through the generated 3c2e kernels: (a|b) = (a s0|b), s0 = unit s function with exponent 0
+    // (then p = a, P = A, K_ab = 1 and the 3c2e base integral reduces to the 2c2e one, defs/coulomb.py:157-160
+    // vs :317-323).  Pairs (shell j, s0) in shell order give the rows of the (naux, naux) matrix.
+    SI_CUDA(cudaSetDevice(c->device));
+    if (!b->twoc_orb) {
+        std::vector<int> L = b->L, np = b->nprim;
+        std::vector<double> cen = b->cen, ex = b->exps, co = b->coef;
+        L.push_back(0);
+        np.push_back(1);
+        cen.insert(cen.end(), {0.0, 0.0, 0.0});
+        ex.push_back(0.0);
+        co.push_back(1.0);
+        si_basis* tb = nullptr;
+        int rc = si_basis_create(c, (int)L.size(), L.data(), np.data(), cen.data(), ex.data(), co.data(), &tb);
+        if (rc) return rc;
+        // the pgto radial factor of an exponent-0 function is 0: the dummy keeps coefficient 1 in both variants
+        tb->coef_pgto.back() = 1.0;
+        SI_CUDA(cudaMemcpy(tb->d_coef_pgto + (tb->coef_pgto.size() - 1), &tb->coef_pgto.back(), sizeof(double),
+                           cudaMemcpyHostToDevice));
+        auto* ps = new si_basis::PairSet;
+        rc = build_pair_set(tb, tb->nshell - 1, tb->nshell, ps, true);
+        if (rc) return rc;
+        b->twoc_orb = tb;
+        b->twoc_pairs = ps;
+    }
+    const size_t n = (size_t)b->nbf_sph;
+    int rc = int3c2e_impl(c, b->twoc_orb, b, 0, b->nshell, normalize, SI_LAYOUT_PACKED, b->twoc_pairs, out_dev, n * n, stream);
+    if (rc) return rc;
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+    k_mirror_lower<<<grid, 256, 0, (cudaStream_t)stream>>>(out_dev, (long long)n);
+    c->launches++;
+    SI_CUDA(cudaGetLastError());
+    return SI_OK;
 }
 
 int si_coul(si_context* c, const si_basis* b, int sph, int normalize, int ncharge, const double* xyz, const double* q,
@@ -998,10 +1053,13 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
     si_basis* orb = const_cast<si_basis*>(corb);
     const si_basis* aux = caux;
     if (sb < 0 || se > aux->nshell || sb >= se) return SI_ERR_ARG;
-    if (orb->lmax > c->lmax || aux->lmax > c->lauxmax) return SI_ERR_LMAX;
+    if ((orb->lmax > c->lmax && pset == nullptr) || aux->lmax > c->lauxmax) return SI_ERR_LMAX;
     SI_CUDA(cudaSetDevice(c->device));
-    int rc = build_pair_classes(orb);
-    if (rc) return rc;
+    int rc = SI_OK;
+    if (!pset) {
+        rc = build_pair_classes(orb);
+        if (rc) return rc;
+    }
     const int col_begin = aux->foff_sph[sb];
     const int col_end = (se == aux->nshell) ? aux->nbf_sph : aux->foff_sph[se];
     const long long naux_local = col_end - col_begin;

@@ -36,7 +36,7 @@ def test_generator_covers_all_classes_and_fits_shared_memory():
     from sympleints_b200.codegen import gen3c2e
 
     info = gen3c2e.class_info(4, 5)
-    assert len(info) == 90
+    assert len(info) == 96   # 90 3c2e classes + (5,0|Lc) used by the 2c2e metric
     for cls, g in info.items():
         assert g.WSZ * g.TPW * 8 <= 227 * 1024, cls
         assert g.EPT * g.TPW == 32
