@@ -40,9 +40,10 @@ def needs_build():
 
 def generate_sources():
     """Run the code generator (class-specialised 3c2e kernels) into csrc/generated/."""
-    from .codegen import gen3c2e
+    from .codegen import gen3c2e, gencoul
 
-    return [Path(f) for f in gen3c2e.write_sources(str(GENDIR))]
+    return [Path(f) for f in gen3c2e.write_sources(str(GENDIR))] + \
+           [Path(f) for f in gencoul.write_sources(str(GENDIR))]
 
 
 def _compile_obj(src, obj, verbose):
@@ -56,10 +57,11 @@ def _compile_obj(src, obj, verbose):
 
 def build_library(force=False, verbose=False, jobs=None):
     gen = generate_sources()
-    deps = SOURCES + HEADERS + [CSRC / "si_g3.h", PKG / "codegen" / "gen3c2e.py", GENDIR / "g3_table.inc"] + gen
-    tj = PKG / "codegen" / "tuning.json"
-    if tj.exists():
-        deps.append(tj)
+    deps = SOURCES + HEADERS + [CSRC / "si_g3.h", PKG / "codegen" / "gen3c2e.py", PKG / "codegen" / "gencoul.py",
+                                GENDIR / "g3_table.inc", GENDIR / "gc_table.inc"] + gen
+    for tj in (PKG / "codegen" / "tuning.json", PKG / "codegen" / "tuning_coul.json"):
+        if tj.exists():
+            deps.append(tj)
     if not force and LIB.exists() and all(p.stat().st_mtime <= LIB.stat().st_mtime for p in deps):
         return LIB
     LIBDIR.mkdir(exist_ok=True)
@@ -74,7 +76,8 @@ def build_library(force=False, verbose=False, jobs=None):
         obj = OBJDIR / (src.stem + ".o")
         objs.append(obj)
         if force or not obj.exists() or obj.stat().st_mtime < max(src.stat().st_mtime, hdr_time) or \
-                (src.name == "si_lib.cu" and obj.stat().st_mtime < (GENDIR / "g3_table.inc").stat().st_mtime):
+                (src.name == "si_lib.cu" and obj.stat().st_mtime < max((GENDIR / "g3_table.inc").stat().st_mtime,
+                                                                        (GENDIR / "gc_table.inc").stat().st_mtime)):
             todo.append((src, obj))
     jobs = jobs or max(1, min(8, (os.cpu_count() or 2)))
     with cf.ThreadPoolExecutor(jobs) as ex:

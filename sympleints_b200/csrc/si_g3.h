@@ -64,6 +64,22 @@ struct G3Args {
     SiBoys boys;
 };
 
+// generated nuclear-attraction kernels (codegen/gencoul.py): one tuple per shell pair, all charges inside
+struct GCArgs {
+    const SiPairItem* pairs;
+    const double* ppair;   // as in G3Args
+    int npairs;
+    const double* cxyz;    // ncharge x 3
+    const double* cq;      // ncharge
+    int ncharge;
+    int nsplit;            // charge ranges per pair: split 0 writes od.out, split sp >= 1 slice sp-1 of `part`
+    double* part;          // (nsplit_max - 1) zero-initialised nbf x nbf slices, summed into od.out afterwards
+    long long ngroups;     // ceil(npairs / pairs-per-warp) * nsplit
+    OutDesc od;            // matrix: out[(fa0+ia) * ld + fb0+jb]
+    int* counter;
+    SiBoys boys;
+};
+
 #if defined(SI_G3_HOST_EMU)
 // ------------------------------------------------------------------ host warp emulation
 #include <algorithm>

@@ -26,6 +26,7 @@
 #include "si_machine.h"
 #include "si_program.h"
 #include "generated/g3_table.inc"
+#include "generated/gc_table.inc"
 
 // ---------------------------------------------------------------------------
 // device-side data
@@ -336,7 +337,25 @@ struct si_context {
     cudaEvent_t ev_join[SI_NSTREAMS];
     int* d_counters = nullptr;
     int next_counter = 0;
+    // grow-only device scratch of the coul path (charges + charge-split partial matrices): no per-call
+    // allocation, whose cost through the stream-ordered pool varies by orders of magnitude
+    double* d_scratch = nullptr;
+    size_t scratch_doubles = 0;
 };
+
+static int ctx_scratch(si_context* c, size_t ndoubles, cudaStream_t s, double** out) {
+    if (ndoubles > c->scratch_doubles) {
+        SI_CUDA(cudaStreamSynchronize(s));
+        SI_CUDA(cudaDeviceSynchronize());
+        if (c->d_scratch) SI_CUDA(cudaFree(c->d_scratch));
+        c->d_scratch = nullptr;
+        c->scratch_doubles = 0;
+        SI_CUDA(cudaMalloc((void**)&c->d_scratch, ndoubles * sizeof(double)));
+        c->scratch_doubles = ndoubles;
+    }
+    *out = c->d_scratch;
+    return SI_OK;
+}
 
 struct si_basis {
     si_context* ctx = nullptr;
@@ -506,6 +525,7 @@ int si_finalize(si_context* c) {
     cudaFree(c->d_boys);
     cudaFree(c->d_pref);
     cudaFree(c->d_counters);
+    cudaFree(c->d_scratch);
     delete c;
     return SI_OK;
 }
@@ -919,6 +939,14 @@ int si_int1e(si_context* c, const si_basis* b, int key, int sph, int normalize, 
 static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* caux, int sb, int se, int normalize,
                         int layout, const si_basis::PairSet* pset, double* out_dev, size_t out_len, void* stream);
 static bool g3_disabled();
+static bool g3_config(const si_context* c, const int* g3, long long ngroups, int* grid, int* block, size_t* smem);
+static const int* gc_find(int La, int Lb) {
+    const int id = La * 10 + Lb;
+    const int n = (int)(sizeof(gc_table) / sizeof(gc_table[0]));
+    for (int i = 0; i < n; ++i)
+        if (gc_table[i][0] == id) return gc_table[i];
+    return nullptr;
+}
 
 int si_int2c2e(si_context* c, const si_basis* b, int sph, int normalize, double* out_dev, void* stream) {
     if (!c || !b || !out_dev) return SI_ERR_ARG;
@@ -960,19 +988,150 @@ int si_int2c2e(si_context* c, const si_basis* b, int sph, int normalize, double*
     return SI_OK;
 }
 
+#define SI_GC_MAX_SPLIT 8
+// out[i] += sum_{sp >= 1} part[sp - 1][i] in a fixed order (charge-split partial matrices of the coul kernels)
+__global__ void k_sum_slices(double* out, const double* part, long long n, int nslices) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = out[i];
+    for (int sp = 0; sp < nslices; ++sp) v += part[(long long)sp * n + i];
+    out[i] = v;
+}
+
+// Nuclear attraction through the generated McMurchie-Davidson kernels (codegen/gencoul.py): one tuple per
+// shell pair, all charges inside; every class on its own stream so that the tails overlap.
+static int run_coul_generated(si_context* c, const si_basis* cb, int normalize, int ncharge, const double* d_cxyz,
+                              const double* d_q, double* out_dev, cudaStream_t user) {
+    si_basis* b = const_cast<si_basis*>(cb);
+    int rc = build_pair_classes(b);
+    if (rc) return rc;
+    if (b->lmax > c->lmax) {
+        g_last_error = "basis angular momentum exceeds the context limit for this key";
+        return SI_ERR_LMAX;
+    }
+    const long long nbf = b->nbf_sph;
+    OutDesc od;
+    od.out = out_dev;
+    od.ld = nbf;
+    od.comp_stride = nbf * nbf;
+    od.nbf = nbf;
+    od.mode = STORE_MATRIX;
+    // Charge split: a class with few shell pairs would leave most SMs idle, so its charges are divided over
+    // nsplit tuples per pair; split 0 writes `out`, split sp >= 1 the slice sp-1 of a zeroed scratch buffer.
+    static int target_warps = -1, max_split = SI_GC_MAX_SPLIT;
+    if (target_warps < 0) {
+        const char* e = getenv("SI_GC_WARPS_PER_SM");
+        target_warps = c->sm_count * (e ? std::max(1, atoi(e)) : 8);
+        const char* m = getenv("SI_GC_MAX_SPLIT");
+        if (m) max_split = std::max(1, std::min(SI_GC_MAX_SPLIT, atoi(m)));
+    }
+    std::vector<int> nsplits;
+    int top_split = 1;
+    for (auto& pc : b->full.classes) {
+        const int* gc = gc_find(pc.La, pc.Lb);
+        if (!gc) return SI_ERR_INTERNAL;
+        const long long pg = (pc.n + gc[3] - 1) / gc[3];
+        int ns = (int)std::min<long long>(std::min(max_split, std::max(1, ncharge / 16)), (target_warps + pg - 1) / pg);
+        ns = std::max(1, ns);
+        nsplits.push_back(ns);
+        top_split = std::max(top_split, ns);
+    }
+    double* d_part = nullptr;
+    if (top_split > 1) {
+        // the charges occupy the first 4 * ncharge doubles of the context scratch (si_coul)
+        double* base = nullptr;
+        rc = ctx_scratch(c, (size_t)4 * ncharge + (size_t)(top_split - 1) * nbf * nbf, user, &base);
+        if (rc) return rc;
+        if (base + 0 != d_cxyz) {
+            g_last_error = "coul scratch moved";
+            return SI_ERR_INTERNAL;
+        }
+        d_part = base + (size_t)4 * ncharge;
+        SI_CUDA(cudaMemsetAsync(d_part, 0, (size_t)(top_split - 1) * nbf * nbf * sizeof(double), user));
+    }
+    static int profile = -1;   // SI_GC_PROFILE=1: classes one after the other, each timed (tuning only)
+    if (profile < 0) {
+        const char* e = getenv("SI_GC_PROFILE");
+        profile = (e && e[0] == '1') ? 1 : 0;
+    }
+    Fan fan{c, user};
+    rc = fan.begin();
+    if (rc) return rc;
+    size_t ci = 0;
+    for (auto& pc : b->full.classes) {
+        const int* gc = gc_find(pc.La, pc.Lb);
+        cudaStream_t s;
+        if (profile) {
+            s = user;
+        } else {
+            rc = fan.stream(&s);
+            if (rc) return rc;
+        }
+        GCArgs ga;
+        ga.pairs = pc.d_items;
+        ga.ppair = b->full.d_ppair[normalize == SI_NORM_PGTO ? 1 : 0];
+        ga.npairs = pc.n;
+        ga.cxyz = d_cxyz;
+        ga.cq = d_q;
+        ga.ncharge = ncharge;
+        ga.nsplit = nsplits[ci++];
+        ga.ngroups = (long long)((pc.n + gc[3] - 1) / gc[3]) * ga.nsplit;
+        ga.od = od;
+        ga.part = d_part;
+        ga.counter = c->d_counters + (c->next_counter++ % SI_NCOUNTERS);
+        ga.boys = c->boys_dev;
+        int grid, block;
+        size_t smem;
+        if (!g3_config(c, gc, ga.ngroups, &grid, &block, &smem)) return SI_ERR_INTERNAL;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (profile) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, s);
+        }
+        if (gc_launch(gc[1], gc[0], ga, grid, block, smem, c->max_smem, s)) return SI_ERR_INTERNAL;
+        c->launches++;
+        SI_CUDA(cudaGetLastError());
+        if (profile) {
+            cudaEventRecord(e1, s);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            fprintf(stderr, "GCPROF %d%d %.4f nsplit=%d grid=%d pairs=%d\n", pc.La, pc.Lb, ms, ga.nsplit, grid, pc.n);
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
+    }
+    rc = fan.end();
+    if (rc) return rc;
+    if (d_part) {
+        const long long n = nbf * nbf;
+        k_sum_slices<<<(unsigned)((n + 255) / 256), 256, 0, user>>>(out_dev, d_part, n, top_split - 1);
+        c->launches++;
+        SI_CUDA(cudaGetLastError());
+    }
+    return SI_OK;
+}
+
 int si_coul(si_context* c, const si_basis* b, int sph, int normalize, int ncharge, const double* xyz, const double* q,
             double* out_dev, void* stream) {
     if (!c || !b || !out_dev || ncharge <= 0 || !xyz || !q) return SI_ERR_ARG;
     SI_CUDA(cudaSetDevice(c->device));
-    double *dx = nullptr, *dq = nullptr;
     cudaStream_t s = (cudaStream_t)stream;
-    SI_CUDA(cudaMallocAsync((void**)&dx, (size_t)ncharge * 3 * sizeof(double), s));
-    SI_CUDA(cudaMallocAsync((void**)&dq, (size_t)ncharge * sizeof(double), s));
+    const bool generated = sph && normalize != SI_NORM_NONE && !g3_disabled() && b->lmax <= 4;
+    // scratch: [xyz 3n][q n][partial matrices of the charge split]; sized for the largest split up front so
+    // that it does not move between the copy of the charges and the launches
+    const size_t nbf = (size_t)b->nbf_sph;
+    double* dx = nullptr;
+    int rc = ctx_scratch(c, (size_t)4 * ncharge + (generated ? (size_t)(SI_GC_MAX_SPLIT - 1) * nbf * nbf : 0), s, &dx);
+    if (rc) return rc;
+    double* dq = dx + (size_t)3 * ncharge;
     SI_CUDA(cudaMemcpyAsync(dx, xyz, (size_t)ncharge * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
     SI_CUDA(cudaMemcpyAsync(dq, q, (size_t)ncharge * sizeof(double), cudaMemcpyHostToDevice, s));
-    int rc = run_two_index(c, b, SI_COUL, sph, normalize, nullptr, ncharge, dx, dq, out_dev, s);
-    cudaFreeAsync(dx, s);
-    cudaFreeAsync(dq, s);
+    if (generated)
+        rc = run_coul_generated(c, b, normalize, ncharge, dx, dq, out_dev, s);
+    else
+        rc = run_two_index(c, b, SI_COUL, sph, normalize, nullptr, ncharge, dx, dq, out_dev, s);
     return rc;
 }
 

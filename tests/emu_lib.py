@@ -138,3 +138,50 @@ def g3_eval(La, Lb, Lc, shell_a, shell_b, aux_shells, table=None):
                              table.shape[0], table.shape[1], _p(pref), _p(res))
     assert rc == 0, rc
     return res
+
+
+# ---- warp emulator of the GENERATED nuclear-attraction kernels (tests/emu/gc_emu.cpp) -----------
+GC_EMU_CLASSES = [(a, b) for a in range(5) for b in range(a + 1)]
+_GC = None
+
+
+def gc_lib():
+    global _GC
+    if _GC is not None:
+        return _GC
+    from sympleints_b200.codegen import gencoul
+
+    inc = HERE / "emu" / "gc_emu_classes.inc"
+    gencoul.write_emu_source(str(inc), GC_EMU_CLASSES)
+    so = HERE / "emu" / "libgc_emu.so"
+    deps = [inc, HERE / "emu" / "gc_emu.cpp", REPO / "sympleints_b200" / "csrc" / "si_g3.h",
+            REPO / "sympleints_b200" / "csrc" / "si_machine.h"]
+    if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-o", str(so),
+                               str(HERE / "emu" / "gc_emu.cpp")])
+    _GC = ctypes.CDLL(str(so))
+    return _GC
+
+
+def gc_eval(La, Lb, pairs, cxyz, cq, table=None, nsplit=1):
+    """pairs: list of (shell_a, shell_b), shell = (exps, coeffs, center), all of class (La >= Lb).
+    Returns array (npairs, nsa, nsb) = sum_C q_C (a|1/r_C|b)."""
+    if table is None:
+        from oracle import boys as oboys
+        table = oboys.table()
+    table = np.ascontiguousarray(table)
+    pref = xlarge_pref(table.shape[0] - 7)
+    ip = ctypes.POINTER(ctypes.c_int)
+    Ka = np.array([len(p[0][0]) for p in pairs], dtype=np.int32)
+    Kb = np.array([len(p[1][0]) for p in pairs], dtype=np.int32)
+    cat = lambda i, j: np.ascontiguousarray(np.concatenate([np.asarray(p[i][j], dtype=float).ravel() for p in pairs]))
+    ax, da, A = cat(0, 0), cat(0, 1), cat(0, 2)
+    bx, db, B = cat(1, 0), cat(1, 1), cat(1, 2)
+    cxyz = np.ascontiguousarray(cxyz, dtype=float).reshape(-1, 3)
+    cq = np.ascontiguousarray(cq, dtype=float)
+    res = np.zeros((len(pairs), 2 * La + 1, 2 * Lb + 1))
+    rc = gc_lib().gcemu_eval(La, Lb, len(pairs), Ka.ctypes.data_as(ip), _p(ax), _p(da), _p(A), Kb.ctypes.data_as(ip),
+                             _p(bx), _p(db), _p(B), len(cq), _p(cxyz), _p(cq), _p(table), table.shape[0],
+                             table.shape[1], _p(pref), nsplit, _p(res))
+    assert rc == 0, rc
+    return res

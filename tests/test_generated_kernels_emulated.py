@@ -40,3 +40,44 @@ def test_generator_covers_all_classes_and_fits_shared_memory():
     for cls, g in info.items():
         assert g.WSZ * g.TPW * 8 <= 227 * 1024, cls
         assert g.EPT * g.TPW == 32
+
+
+# ---- generated nuclear-attraction kernels (codegen/gencoul.py, McMurchie-Davidson) -----------------
+@pytest.mark.parametrize("Ls", emu_lib.GC_EMU_CLASSES)
+def test_generated_coul_class_vs_oracle(Ls):
+    La, Lb = Ls
+    rng = np.random.default_rng(10 * La + Lb)
+    # several shell pairs with different contraction lengths share a warp (pairs-per-warp packing, the
+    # padded primitive-pair loop, the "repeat last valid pair" path); several charges per pair
+    pairs = [(_shell(rng, La, int(ka)), _shell(rng, Lb, int(kb))) for ka, kb in ((1, 1), (2, 3), (3, 1), (1, 2), (2, 2))]
+    xyz = rng.uniform(-2, 2, (5, 3))
+    q = rng.uniform(-3, 3, 5)
+    g = emu_lib.gc_eval(La, Lb, pairs, xyz, q)
+    for k, (sa, sb) in enumerate(pairs):
+        o = sum(qq * ints.coul(La, Lb, *sa, *sb, R=rr) for rr, qq in zip(xyz, q)).reshape(g[k].shape)
+        assert np.abs(o - g[k]).max() <= 1e-14 + 1e-12 * np.abs(o).max(), (Ls, k)
+    # charges split over 3 tuples per pair (partial matrices summed afterwards)
+    g3 = emu_lib.gc_eval(La, Lb, pairs, xyz, q, nsplit=3)
+    assert np.abs(g3 - g).max() <= 1e-13 * np.abs(g).max()
+
+
+def test_generated_coul_vs_golden_blocks():
+    """Per-block parity criterion against the reference's own output (tests/golden), incl. the (g|g)
+    block with very unequal exponents that a VRR+HRR evaluation fails."""
+    import golden_util as gu
+
+    sph, normalize, blocks = gu.load_variant("sph_cgto_l4_laux5")
+    n = 0
+    for blk in blocks:
+        if blk["key"] != "coul":
+            continue
+        La, Lb = blk["Ls"]
+        R = blk["R"].reshape(1, 3)
+        if La >= Lb:
+            got = emu_lib.gc_eval(La, Lb, [(blk["a"], blk["b"])], R, np.ones(1))[0]
+        else:
+            got = emu_lib.gc_eval(Lb, La, [(blk["b"], blk["a"])], R, np.ones(1))[0].T
+        ok, rep = gu.block_error(got.reshape(blk["ref64"].shape), blk)
+        assert ok, rep
+        n += 1
+    assert n >= 15

@@ -73,13 +73,33 @@ def test_nuclear_attraction_with_point_charges(engine, small):
     shells, sites, _, ob, _ = small
     xyz, q = synthetic.point_charges(sites, n=24, seed=3)
     g = engine.coul(ob, xyz, q).cpu().numpy()
-    o = sum(qq * oracle_matrix("coul", shells, R=rr)[0] for rr, qq in zip(xyz, q))
+    os_ = [oracle_matrix("coul", shells, R=rr)[0] for rr in xyz]
+    o = sum(qq * oc for oc, qq in zip(os_, q))
     assert np.abs(g - o).max() <= 1e-14 + 1e-12 * np.abs(o).max()
     h = engine.coul_host(ob, xyz, q)
     assert np.array_equal(h, g)
     # linearity in the charges
     g2 = engine.coul(ob, xyz, 2.0 * q).cpu().numpy()
     assert np.abs(g2 - 2 * g).max() <= 1e-13 * np.abs(g).max()
+    # mirrored exactly
+    assert np.abs(g - g.T).max() <= 1e-15 * np.abs(g).max()
+    # every shell-pair block on its own scale (generated McMurchie-Davidson kernels, all 15 classes)
+    off = np.concatenate([[0], np.cumsum(_sizes(shells, True))])
+    for i in range(len(shells)):
+        for j in range(len(shells)):
+            blk = (slice(off[i], off[i + 1]), slice(off[j], off[j + 1]))
+            tol = sum(abs(qq) * (1e-14 + 1e-12 * np.abs(oc[blk]).max()) for oc, qq in zip(os_, q))
+            assert np.abs(g[blk] - o[blk]).max() <= tol, (i, j)
+
+
+@pytest.mark.parametrize("sph,normalize", [(True, "pgto"), (False, "cgto"), (True, "none")])
+def test_nuclear_attraction_other_variants(engine, small, sph, normalize):
+    """pgto goes through the generated kernels, Cartesian / un-normalised output through the stage machine."""
+    shells, sites, _, ob, _ = small
+    xyz, q = synthetic.point_charges(sites, n=5, seed=4)
+    g = engine.coul(ob, xyz, q, sph=sph, normalize=normalize).cpu().numpy()
+    o = sum(qq * oracle_matrix("coul", shells, sph=sph, normalize=normalize, R=rr)[0] for rr, qq in zip(xyz, q))
+    assert np.abs(g - o).max() <= 1e-14 + 1e-12 * np.abs(o).max()
 
 
 def _oracle_3c_block(a, b, c):
