@@ -835,6 +835,7 @@ struct Fan {
     si_context* c;
     cudaStream_t user;
     int next = 0;
+    int limit = SI_NSTREAMS;   // streams used by this fan
     bool used[SI_NSTREAMS];
     int begin() {
         memset(used, 0, sizeof(used));
@@ -849,7 +850,7 @@ struct Fan {
             const char* e = getenv("SI_NSTREAMS");
             nstreams = e ? std::max(1, std::min(SI_NSTREAMS, atoi(e))) : SI_NSTREAMS;
         }
-        int i = next++ % nstreams;
+        int i = next++ % std::min(nstreams, limit);
         if (!used[i]) {
             SI_CUDA(cudaStreamWaitEvent(c->streams[i], c->ev_fork, 0));
             used[i] = true;
@@ -1194,7 +1195,12 @@ static bool g3_config(const si_context* c, const int* g3, long long ngroups, int
     if (nw < 1) return false;
     *block = nw * 32;
     *smem = per_warp * nw;
-    *grid = (int)std::max<long long>(1, std::min<long long>((ngroups + nw - 1) / nw, (long long)c->sm_count * 16));
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        const char* e = getenv("SI_G3_GRID_PER_SM");
+        per_sm = e ? std::max(1, atoi(e)) : 4;   // persistent blocks: at most 4 x 4 warps are resident per SM
+    }
+    *grid = (int)std::max<long long>(1, std::min<long long>((ngroups + nw - 1) / nw, (long long)c->sm_count * per_sm));
     return true;
 }
 
@@ -1279,6 +1285,7 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
     BasisDev od_orb = basis_dev(orb, 1, normalize);
     BasisDev od_aux = basis_dev(aux, 1, normalize);
     Fan fan{c, user};
+    fan.limit = 2;
     rc = fan.begin();
     if (rc) return rc;
     // heaviest classes first
@@ -1310,7 +1317,15 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
             const char* e = getenv("SI_FORCE_FAN");
             force_fan = (e && e[0] == '1') ? 1 : 0;
         }
-        const bool big = !force_fan && (long long)job.pc->n * sp.second >= (long long)c->sm_count * 64;
+        // "big" = long enough that its tail (one shell-tuple latency, 20-100 us) does not matter; shorter
+        // launches (small systems, one rank's shard of many) alternate between two streams so that the
+        // next kernel's blocks fill the tail of the previous one
+        static double big_flops = -1.0;
+        if (big_flops < 0) {
+            const char* e = getenv("SI_G3_BIG_FLOPS");
+            big_flops = e ? atof(e) : 2.5e8;
+        }
+        const bool big = !force_fan && 2.0 * job.cost >= big_flops;
         if (big) fan.next = 0;
         rc = fan.stream(&s);
         if (rc) return rc;
