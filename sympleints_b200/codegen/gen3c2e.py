@@ -244,8 +244,12 @@ class ClassGen:
             self.Z_OFF = prim_start
             z_end = prim_start + self.nm * self.ZS
         w = max(prim_end, z_end)
-        if w % 2 == 0:
-            w += 1               # odd stride: conflict-free when several tuples share a warp
+        # Several tuples share a warp when EPT < 32; a half-warp (one shared-memory wavefront of 8-byte
+        # accesses, 16 banks) then holds 16/EPT tuples whose lanes touch ~EPT consecutive words each, so the
+        # tuple stride must be an odd multiple of EPT modulo 16 for the tuples to tile the banks
+        e = self.EPT if self.EPT <= 8 else 1    # (EPT >= 16: the tuples of a warp sit in different half-warps)
+        while w % (2 * e) != e:
+            w += 1
         self.WSZ = w
 
     def _conflicts(self):

@@ -98,7 +98,9 @@ class CoulGen:
         o += self.nca * self.nsb
         end3 = o
         o = max(end1, end2, end3)
-        if o % 2 == 0:
+        # tuple stride = odd multiple of EPT modulo 16 (see gen3c2e.ClassGen._layout)
+        e = self.EPT if self.EPT <= 8 else 1    # (EPT >= 16: the tuples of a warp sit in different half-warps)
+        while o % (2 * e) != e:
             o += 1
         self.WSZ = o
 

@@ -328,6 +328,7 @@ struct si_context {
     std::vector<double> pref_host;
     int nrows = 0, ncols = 0;
     double* d_boys = nullptr;
+    double* d_boysT = nullptr;
     double* d_pref = nullptr;
     SiBoys boys_dev;
     std::map<std::tuple<int, int, int, int, int, int>, DevProgram*> progs;
@@ -488,6 +489,14 @@ int si_init(int device, int lmax, int lauxmax, const double* boys_table, int nro
     SI_CUDA(cudaMemcpy(c->d_boys, c->boys_host.data(), c->boys_host.size() * sizeof(double), cudaMemcpyHostToDevice));
     SI_CUDA(cudaMalloc(&c->d_pref, c->pref_host.size() * sizeof(double)));
     SI_CUDA(cudaMemcpy(c->d_pref, c->pref_host.data(), c->pref_host.size() * sizeof(double), cudaMemcpyHostToDevice));
+    {
+        std::vector<double> tT((size_t)c->nrows * c->ncols);
+        for (int r = 0; r < c->nrows; ++r)
+            for (int i = 0; i < c->ncols; ++i) tT[(size_t)i * c->nrows + r] = c->boys_host[(size_t)r * c->ncols + i];
+        SI_CUDA(cudaMalloc(&c->d_boysT, tT.size() * sizeof(double)));
+        SI_CUDA(cudaMemcpy(c->d_boysT, tT.data(), tT.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    c->boys_dev.tableT = c->d_boysT;
     c->boys_dev.table = c->d_boys;
     c->boys_dev.xlarge_pref = c->d_pref;
     c->boys_dev.nrows = c->nrows;
@@ -525,6 +534,7 @@ int si_finalize(si_context* c) {
     cudaFree(c->d_boys);
     cudaFree(c->d_pref);
     cudaFree(c->d_counters);
+    cudaFree(c->d_boysT);
     cudaFree(c->d_scratch);
     delete c;
     return SI_OK;

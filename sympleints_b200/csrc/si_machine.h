@@ -160,6 +160,9 @@ struct SiBoys {
     const double* table;   // (nmax + 7) x 301
     const double* xlarge_pref;  // (2n-1)!!/2^(n+1) sqrt(pi), n = 0..nmax
     int32_t nrows, ncols;
+    // the same table transposed, 301 x (nmax + 7): the six Taylor coefficients F_n..F_{n+5} of one grid
+    // point are contiguous (one or two cache lines instead of six), and all orders of one tuple share them
+    const double* tableT;
 };
 
 SI_HD double si_boys(const SiBoys& B, int n, double x) {
@@ -195,17 +198,17 @@ SI_HD double si_boys(const SiBoys& B, int n, double x) {
 // x^(-n-1/2) = sqrt(1/x) (1/x)^n by binary exponentiation instead of pow() (differences ~1e-16 relative).
 SI_HD double si_boys_fast(const SiBoys& B, int n, double x) {
     if (x < 30.0) {
-        if (x == 0.0) return B.table[n * B.ncols];
+        // (x == 0 gives ind0 = 0, mdx = 0 and the sum reduces to the tabulated F_n(0) exactly)
         const int ind0 = (int)(x * 10.0);
         const double mdx = ind0 * 0.1 - x;
-        const double* t = B.table + n * B.ncols + ind0;
-        const int nc = B.ncols;
-        double r = t[5 * nc] * (1.0 / 120.0);
-        r = fma(r, mdx, t[4 * nc] * (1.0 / 24.0));
-        r = fma(r, mdx, t[3 * nc] * (1.0 / 6.0));
-        r = fma(r, mdx, t[2 * nc] * 0.5);
-        r = fma(r, mdx, t[nc]);
-        r = fma(r, mdx, t[0]);
+        const double* t = B.tableT + ind0 * B.nrows + n;
+        const double t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3], t4 = t[4], t5 = t[5];
+        double r = t5 * (1.0 / 120.0);
+        r = fma(r, mdx, t4 * (1.0 / 24.0));
+        r = fma(r, mdx, t3 * (1.0 / 6.0));
+        r = fma(r, mdx, t2 * 0.5);
+        r = fma(r, mdx, t1);
+        r = fma(r, mdx, t0);
         return r;
     }
     const double inv = 1.0 / x;

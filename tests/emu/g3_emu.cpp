@@ -103,6 +103,10 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
     args.od.mode = STORE_3C_FULL;
     int counter = 0;
     args.counter = &counter;
+    std::vector<double> boys_T((size_t)nrows * ncols);
+    for (int r = 0; r < nrows; ++r)
+        for (int i = 0; i < ncols; ++i) boys_T[(size_t)i * nrows + r] = boys_table[(size_t)r * ncols + i];
+    args.boys.tableT = boys_T.data();
     args.boys.table = boys_table;
     args.boys.xlarge_pref = xlarge_pref;
     args.boys.nrows = nrows;

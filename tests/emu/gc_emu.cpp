@@ -81,6 +81,10 @@ extern "C" int gcemu_eval(int La, int Lb, int npairs, const int* Ka, const doubl
     args.od.mode = STORE_MATRIX;
     int counter = 0;
     args.counter = &counter;
+    std::vector<double> boys_T((size_t)nrows * ncols);
+    for (int r = 0; r < nrows; ++r)
+        for (int i = 0; i < ncols; ++i) boys_T[(size_t)i * nrows + r] = boys_table[(size_t)r * ncols + i];
+    args.boys.tableT = boys_T.data();
     args.boys.table = boys_table;
     args.boys.xlarge_pref = xlarge_pref;
     args.boys.nrows = nrows;

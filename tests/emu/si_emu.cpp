@@ -79,6 +79,7 @@ int siemu_eval(int key, int La, int Lb, int Lc, int sph, int normalize, int Ka, 
         const SiProg& P = c->prog;
         SiBoys Bt;
         Bt.table = boys_table;
+        Bt.tableT = nullptr;
         Bt.xlarge_pref = xlarge_pref;
         Bt.nrows = nrows;
         Bt.ncols = ncols;
