@@ -430,7 +430,9 @@ class ClassGen:
         self.open("for (;;)")
         E("const long long ch = ch_next;")
         E("if (ch * A.chunk >= A.ngroups) break;")
-        E("ch_next = si_g3_fetch_group(A.counter, lane);   // raw atomic result of lane 0, broadcast at the chunk end")
+        E("// raw atomic result of lane 0 (nothing may consume it before the chunk end, or the warp would wait")
+        E("// for the round trip right here)")
+        E("const int ch_raw = si_g3_fetch_group(A.counter, lane);")
         E("const long long g_end = min((ch + 1) * (long long)A.chunk, A.ngroups);")
         self.open("for (long long grp = ch * A.chunk; grp < g_end; ++grp)")
         E("// group -> (pair, first aux of the group); tuples beyond the run end recompute the last valid one")
@@ -486,7 +488,7 @@ class ClassGen:
             E("if (valid && q == 0) A.od.out[0] = W[0];")
         self.sync()
         self.close()  # groups of the chunk
-        E("ch_next = si_g3_bcast_group(ch_next);")
+        E("ch_next = si_g3_bcast_group(ch_raw);")
         self.close()  # for(;;)
         self.close()  # function
         E("")
@@ -750,7 +752,7 @@ class ClassGen:
         targets = [node([0, 0, 0], list(b)) for b in cart_order(Lb)]
         self.open(f"for (int item = q; item < {nit}; item += EPT)")
         E(f"const int ai = item / {nm}, m = item - ai * {nm};")
-        E("int ia_ = 0; while ((ia_ + 1) * (ia_ + 2) / 2 <= ai) ++ia_;   // row of the target a (l = La - ia_)")
+        E("const int ia_ = si_g3_tri_row(ai);   // row of the target a (l = La - ia_)")
         E(f"const int yb = {self.Y_OFF} + m * {self.YS} + ai;")
         for ik in range(Lb + 1):
             E(f"const int yb{ik} = yb + ia_ * {ik};")
@@ -801,9 +803,16 @@ class ClassGen:
                 coef = Ma[ia][a] * fa[a]
                 expr = f"{lit(coef)} * z{a}" if expr is None else f"fma({lit(coef)}, z{a}, {expr})"
             E(f"const double o{ia} = {expr};")
+        # one address computation per item: element ia lives at p0 + ia * s0 (and its mirror at p1 + ia * s1)
+        E(f"double* p0; long long s0; double* p1 = nullptr; long long s1 = 0;")
+        E(f"si_g3_store_setup(A.od, it, fa0, fb0, {nsa}, {nsb}, {nm}, col, jb, m, &p0, &s0, &p1, &s1);")
         self.open("if (valid)")
         for ia in range(nsa):
-            E(f"si_g3_store(A.od, it, fa0, fb0, {nsa}, {nsb}, {nm}, col, {ia}, jb, m, o{ia});")
+            E(f"p0[{ia} * s0] = o{ia};")
+        self.open("if (p1)")
+        for ia in range(nsa):
+            E(f"p1[{ia} * s1] = o{ia};")
+        self.close()
         self.close()
         self.close()
 

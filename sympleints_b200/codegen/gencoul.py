@@ -178,7 +178,7 @@ class CoulGen:
         self.open("for (;;)")
         E("const long long grp = g_next;")
         E("if (grp >= A.ngroups) break;")
-        E("g_next = si_g3_fetch_group(A.counter, lane);")
+        E("const int g_raw = si_g3_fetch_group(A.counter, lane);   // consumed only at the end of the group")
         E("// group -> (pair group, charge split): the charges are divided over A.nsplit tuples per pair, each")
         E("// writing its partial matrix slice; the slices are summed in a fixed order afterwards")
         E("const int pg = (int)(grp / A.nsplit), sp = (int)(grp - (long long)pg * A.nsplit);")
@@ -365,7 +365,7 @@ class CoulGen:
         self.close()
         self.close()
         self.sync()
-        E("g_next = si_g3_bcast_group(g_next);")
+        E("g_next = si_g3_bcast_group(g_raw);")
         self.close()  # for(;;)
         self.close()  # function
         E("")

@@ -125,10 +125,15 @@ static inline long long si_g3_next_group(int* counter, int lane) {
     si_g3_syncwarp();
     return v;
 }
-static inline long long si_g3_fetch_group(int* counter, int lane) {
-    return lane == 0 ? (long long)__atomic_fetch_add(counter, 1, __ATOMIC_SEQ_CST) : 0;
+static inline int si_g3_fetch_group(int* counter, int lane) {
+    return lane == 0 ? __atomic_fetch_add(counter, 1, __ATOMIC_SEQ_CST) : 0;
 }
-static inline long long si_g3_bcast_group(long long v) {
+static inline int si_g3_tri_row(int ai) {
+    int r = 0;
+    while ((r + 1) * (r + 2) / 2 <= ai) ++r;
+    return r;
+}
+static inline long long si_g3_bcast_group(int v) {
     if (si_g3_emu_lane == 0) si_g3_emu_warp->xchg[0] = v;
     si_g3_syncwarp();
     long long r = si_g3_emu_warp->xchg[0];
@@ -159,16 +164,43 @@ __device__ __forceinline__ long long si_g3_next_group(int* counter, int lane) {
     if (lane == 0) v = atomicAdd(counter, 1);
     return (long long)__shfl_sync(0xffffffffu, v, 0);
 }
-__device__ __forceinline__ long long si_g3_fetch_group(int* counter, int lane) {
+__device__ __forceinline__ int si_g3_fetch_group(int* counter, int lane) {
     int v = 0;
     if (lane == 0) v = atomicAdd(counter, 1);
-    return (long long)v;
+    return v;
 }
-__device__ __forceinline__ long long si_g3_bcast_group(long long v) {
-    return (long long)__shfl_sync(0xffffffffu, (int)v, 0);
+__device__ __forceinline__ long long si_g3_bcast_group(int v) {
+    return (long long)__shfl_sync(0xffffffffu, v, 0);
+}
+// row r of the triangular index ai = r (r + 1) / 2 + c, 0 <= c <= r (ai < 2^20: exact in float)
+__device__ __forceinline__ int si_g3_tri_row(int ai) {
+    return (int)((__fsqrt_rn(8.0f * (float)ai + 1.0f) - 1.0f) * 0.5f);
 }
 __device__ __forceinline__ int si_g3_warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 #endif
+
+// addressing of the elements (ia = 0..nsa-1, jb, m) of the (a_sph, b_sph, c_sph) block of pair item `it`:
+// element ia at p0[ia * s0]; in the full layout the mirror image (b, a) at p1[ia * s1] (p1 = null otherwise)
+SI_HD void si_g3_store_setup(const OutDesc& od, const SiPairItem& it, int fa0, int fb0, int nsa, int nsb, int nm,
+                             long long col, int jb, int m, double** p0, long long* s0, double** p1, long long* s1) {
+    if (od.mode == STORE_BLOCK) {
+        *p0 = od.out + (long long)jb * nm + m;
+        *s0 = (long long)nsb * nm;
+    } else if (od.mode == STORE_3C_FULL) {
+        *p0 = od.out + ((long long)fa0 * od.nbf + (fb0 + jb)) * od.ld + col + m;
+        *s0 = od.nbf * od.ld;
+        if (it.sa != it.sb) {
+            *p1 = od.out + ((long long)(fb0 + jb) * od.nbf + fa0) * od.ld + col + m;
+            *s1 = od.ld;
+        }
+    } else if (it.swapped) {
+        *p0 = od.out + (it.prow + (long long)jb * nsa) * od.ld + col + m;
+        *s0 = od.ld;
+    } else {
+        *p0 = od.out + (it.prow + jb) * od.ld + col + m;
+        *s0 = (long long)nsb * od.ld;
+    }
+}
 
 // element (ia, jb, m) of the (a_sph, b_sph, c_sph) block of pair item `it`
 SI_HD void si_g3_store(const OutDesc& od, const SiPairItem& it, int fa0, int fb0, int nsa, int nsb, int nm,
