@@ -414,8 +414,8 @@ def bench_other_keys(eng, shells, sites, aux, ob, ab, fp64_peak, peaks, reps=5):
     res["coul_1024_charges"] = {"s": t, "integrals_per_s": uniq / t, "integral_charges_per_s": uniq * 1024 / t,
                                 "roofline": {"bound": "fp64", "achieved": flops / t / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                                              "frac": flops / t / 1e12 / fp64_peak if fp64_peak else None,
-                                             "note": "model flops 6.68e10 (SURVEY 8d, VRR+HRR graph); the kernel uses the "
-                                                     "reference's two-index VRR for bitwise-comparable conditioning"}}
+                                             "note": "model flops 6.68e10 (SURVEY 8d, VRR+HRR graph); the generated "
+                                                     "McMurchie-Davidson kernels (codegen/gencoul.py) execute fewer"}}
     return res
 
 

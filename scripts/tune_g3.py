@@ -12,7 +12,7 @@ def build():
     out.mkdir(parents=True, exist_ok=True)
     for sh, mb, yr in VARIANTS:
         env = dict(os.environ, SI_G3_EPT_SHIFT=str(sh), SI_G3_MB=str(mb), SI_G3_YREG=str(yr), SI_G3_NO_TUNING="1")
-        subprocess.check_call([sys.executable, "-c", "from sympleints_b200 import build; build.build_library(force=True)"], cwd=REPO, env=env)
+        subprocess.check_call([sys.executable, "-c", "from sympleints_b200 import build; build.build_library()"], cwd=REPO, env=env)
         shutil.copy(REPO / "sympleints_b200" / "lib" / "libsympleints_b200.so", out / f"lib_sh{sh}_mb{mb}_y{yr}.so")
         print("built", sh, mb, yr, flush=True)
 
