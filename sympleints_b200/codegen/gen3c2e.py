@@ -349,21 +349,45 @@ class ClassGen:
         return tab
 
     def dtree_meta(self):
-        """Per flat index f (shells 0..L): for d in x,y,z: delta to flat index of a-1_d (0 if a_d == 0), a_d."""
-        out = []
+        """Per flat index f (shells 0..L): for d in x,y,z: (f - index read for the a-1_d neighbour, a_d).
+
+        Elements without a neighbour (a_d == 0) multiply whatever they read by 0.  Reading their own index
+        would add a second address stream to the wavefront (bank conflicts), so they are pointed at the
+        neighbour address of the nearest element of their half-warp group that has one (a broadcast)."""
+        flat = []
         for n in range(self.L + 1):
             for a in cart_order(n):
-                f = off(n) + cidx(a)
-                ent = []
-                for d in range(3):
-                    if a[d] > 0:
-                        am = list(a)
-                        am[d] -= 1
-                        fm = off(n - 1) + cidx(am)
-                        ent.append((fm - f, a[d]))
-                    else:
-                        ent.append((0, 0))
-                out.append((n, ent))
+                flat.append((n, a))
+        tgt = []
+        for f, (n, a) in enumerate(flat):
+            row = []
+            for d in range(3):
+                if a[d] > 0:
+                    am = list(a)
+                    am[d] -= 1
+                    row.append(off(n - 1) + cidx(am))
+                else:
+                    row.append(None)
+            tgt.append(row)
+        B = min(self.EPT, 16)
+        lo_top = off(self.La)
+        out = []
+        for f, (n, a) in enumerate(flat):
+            ent = []
+            for d in range(3):
+                if tgt[f][d] is not None:
+                    ent.append((f - tgt[f][d], a[d]))
+                    continue
+                t = f
+                blk = range((f // B) * B, min((f // B) * B + B, self.NA))
+                up = [g for g in blk if g > f and tgt[g][d] is not None]
+                dn = [g for g in blk if g < f and g >= lo_top and tgt[g][d] is not None]
+                if up:
+                    t = tgt[up[0]][d]
+                elif dn:
+                    t = tgt[dn[-1]][d]
+                ent.append((f - t, 0))
+            out.append((n, ent))
         return out
 
     # ---- the generator ----------------------------------------------------------------------
@@ -387,7 +411,8 @@ class ClassGen:
             for (n, ent) in dm:
                 v = 0
                 for d in range(3):
-                    v |= ((-ent[d][0]) & 0xFF) << (8 * d)
+                    assert -16 <= ent[d][0] < 240
+                    v |= ((ent[d][0] + 16) & 0xFF) << (8 * d)
                 v |= (n & 0xF) << 24
                 vals.append(v)
             E(f"__device__ const int g3_dd_{name}[{len(vals)}] = {{{', '.join(map(str, vals))}}};")
@@ -416,7 +441,7 @@ class ClassGen:
             for s in range(nsl_d):
                 E(f"int nx_{s}, ny_{s}, nz_{s}, ds_{s}; double dfx_{s}, dfy_{s}, dfz_{s}; const int fc_{s} = min(q + EPT * {s}, {self.NA - 1}); "
                   f"{{ const int f = fc_{s}; int v = g3_dd_{name}[f]; int w = g3_df_{name}[f]; ds_{s} = (v >> 24) & 0xF; "
-                  f"nx_{s} = f - (v & 0xFF); ny_{s} = f - ((v >> 8) & 0xFF); nz_{s} = f - ((v >> 16) & 0xFF); "
+                  f"nx_{s} = f + 16 - (v & 0xFF); ny_{s} = f + 16 - ((v >> 8) & 0xFF); nz_{s} = f + 16 - ((v >> 16) & 0xFF); "
                   f"dfx_{s} = (double)(w & 0xF); dfy_{s} = (double)((w >> 4) & 0xF); dfz_{s} = (double)((w >> 8) & 0xF); }}")
                 # leaf targets: index into a Y row (clamped) and validity of this lane's element
                 E(f"const bool yv_{s} = (q + EPT * {s} >= {off(La)}) && (q + EPT * {s} < {self.NA}); "
