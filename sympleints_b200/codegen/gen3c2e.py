@@ -201,7 +201,7 @@ class ClassGen:
         if ypad is None:
             best = None
             for yp in range(0, 8):
-                for zp in (range(0, 8) if self.Lb > 0 else [0]):
+                for zp in [0]:
                     self._layout(yp, zp)
                     c = (self._conflicts(), self.WSZ)
                     if best is None or c < best[0]:
@@ -218,9 +218,9 @@ class ClassGen:
         # Y[m][a'] persistent over primitives: the leaves of the aux recurrence are folded straight
         # into the spherical components (C2S on c), so no Cartesian [a0|c] block is ever stored
         self.YS = self.n_ap + ypad                 # stride between m rows of Y
-        self.ZS = self.nca * self.nsb + zpad       # stride between m slabs of Z
-        if self.Lb == 0:
-            self.ZS = self.YS
+        # Z (after HRR + C2S(b)) is laid out [a][jb][m], m fastest: the C2S(a) stage then reads consecutive
+        # words per lane (its items are (jb, m), m fastest, which also keeps the global stores coalesced)
+        self.ZS = self.YS if self.Lb == 0 else None
         self.Y_OFF = o
         o += self.nm * self.YS
         prim_start = o
@@ -242,7 +242,7 @@ class ClassGen:
             z_end = prim_start
         else:
             self.Z_OFF = prim_start
-            z_end = prim_start + self.nm * self.ZS
+            z_end = prim_start + self.nca * self.nsb * self.nm
         w = max(prim_end, z_end)
         # Several tuples share a warp when EPT < 32; a half-warp (one shared-memory wavefront of 8-byte
         # accesses, 16 banks) then holds 16/EPT tuples whose lanes touch ~EPT consecutive words each, so the
@@ -282,7 +282,7 @@ class ClassGen:
                     if item >= nit:
                         lanes.append(None)
                         continue
-                    ai, m = divmod(item, nm)
+                    m, ai = divmod(item, nca)
                     ia = 0
                     while (ia + 1) * (ia + 2) // 2 <= ai:
                         ia += 1
@@ -293,17 +293,18 @@ class ClassGen:
                     total += cost([None if t is None else t[0] * self.WSZ + self.Y_OFF + t[2] * self.YS + t[1] + t[3] * ik + const
                                    for t in lanes])
                 for jb in range(nsb):
-                    total += cost([None if t is None else t[0] * self.WSZ + self.Z_OFF + t[2] * self.ZS + t[1] * nsb + jb
+                    total += cost([None if t is None else t[0] * self.WSZ + self.Z_OFF + (t[1] * nsb + jb) * nm + t[2]
                                    for t in lanes])
-        nit = nsb * nm
-        for r in range((nit + EPT - 1) // EPT):
-            lanes = []
-            for lane in range(32):
-                q, tl = lane % EPT, lane // EPT
-                item = q + EPT * r
-                lanes.append(None if item >= nit else (tl,) + divmod(item, nm))
-            for a in range(nca):
-                total += cost([None if t is None else t[0] * self.WSZ + self.Z_OFF + t[2] * self.ZS + a * nsb + t[1] for t in lanes])
+        else:
+            nit = nsb * nm
+            for r in range((nit + EPT - 1) // EPT):
+                lanes = []
+                for lane in range(32):
+                    q, tl = lane % EPT, lane // EPT
+                    item = q + EPT * r
+                    lanes.append(None if item >= nit else (tl,) + divmod(item, nm))
+                for a in range(nca):
+                    total += cost([None if t is None else t[0] * self.WSZ + self.Z_OFF + t[2] * self.ZS + a * nsb + t[1] for t in lanes])
         return total
 
     # ---- emission helpers ---------------------------------------------------------------
@@ -776,7 +777,7 @@ class ClassGen:
 
         targets = [node([0, 0, 0], list(b)) for b in cart_order(Lb)]
         self.open(f"for (int item = q; item < {nit}; item += EPT)")
-        E(f"const int ai = item / {nm}, m = item - ai * {nm};")
+        E(f"const int m = item / {nca}, ai = item - m * {nca};   // a fastest: near-consecutive shared-memory addresses")
         E("const int ia_ = si_g3_tri_row(ai);   // row of the target a (l = La - ia_)")
         E(f"const int yb = {self.Y_OFF} + m * {self.YS} + ai;")
         for ik in range(Lb + 1):
@@ -803,7 +804,7 @@ class ClassGen:
                 expr = f"{lit(coef)} * {targets[j]}" if expr is None else f"fma({lit(coef)}, {targets[j]}, {expr})"
             E(f"const double zb{jb} = {expr};")
         for jb in range(nsb):
-            E(f"W[{self.Z_OFF} + m * {self.ZS} + ai * {nsb} + {jb}] = zb{jb};")
+            E(f"W[{self.Z_OFF + jb * nm} + ai * {nsb * nm} + m] = zb{jb};")
         self.close()
 
     # ---- C2S(a) + global store --------------------------------------------------------------
@@ -819,7 +820,10 @@ class ClassGen:
         self.open(f"for (int item = q; item < {nit}; item += EPT)")
         E(f"const int jb = item / {nm}, m = item - jb * {nm};")
         for a in range(nca):
-            E(f"const double z{a} = W[{self.Z_OFF} + m * {self.ZS} + {a * nsb} + jb];")
+            if self.Lb > 0:
+                E(f"const double z{a} = W[{self.Z_OFF + a * nsb * nm} + item];")
+            else:
+                E(f"const double z{a} = W[{self.Z_OFF} + m * {self.ZS} + {a * nsb} + jb];")
         for ia in range(nsa):
             expr = None
             for a in range(nca):
