@@ -456,9 +456,7 @@ class ClassGen:
         self.open("for (;;)")
         E("const long long ch = ch_next;")
         E("if (ch * A.chunk >= A.ngroups) break;")
-        E("// raw atomic result of lane 0 (nothing may consume it before the chunk end, or the warp would wait")
-        E("// for the round trip right here)")
-        E("const int ch_raw = si_g3_fetch_group(A.counter, lane);")
+        E("int ch_raw = 0;")
         E("const long long g_end = min((ch + 1) * (long long)A.chunk, A.ngroups);")
         self.open("for (long long grp = ch * A.chunk; grp < g_end; ++grp)")
         E("// group -> (pair, first aux of the group); tuples beyond the run end recompute the last valid one")
@@ -499,6 +497,10 @@ class ClassGen:
         self.close()  # ik
         self.close()  # ib
         self.close()  # ia
+        E("// Fetch the next chunk index now: raw atomic result of lane 0, consumed (broadcast) at the chunk end, so")
+        E("// its round trip overlaps the contracted phase.  (Issued earlier, the result register gets spilled, and")
+        E("// the spill store waits for the atomic.)")
+        E("if (grp + 1 >= g_end) ch_raw = si_g3_fetch_group(A.counter, lane);")
         if self.YREG:
             self.sync("last primitive's readers of the overlaid arrays are done")
             for m in range(self.nm):

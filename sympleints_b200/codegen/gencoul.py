@@ -161,7 +161,7 @@ class CoulGen:
         E(f"__device__ const int gc_ab_{name}[{nab}] = {{{', '.join(map(str, vals))}}};")
         E("")
         E(f"// coul class ({La}{Lb}): EPT={EPT} lanes per shell pair, {TPW} pairs per warp, {self.WSZ} doubles of shared memory per pair")
-        E(f"SI_G3_DEV void gc_body_{name}(const GCArgs& A, const int lane, double* wbase) {{")
+        E(f"SI_G3_DEV void gc_body_{name}(const GCArgs& A, const int lane, double* wbase, const long long g_first, const long long g_stride) {{")
         self.ind = 1
         E(f"constexpr int EPT = {EPT}, TPW = {TPW}, WSZ = {self.WSZ};")
         E("const int q = lane % EPT, tl = lane / EPT;")
@@ -174,11 +174,8 @@ class CoulGen:
         nsl_b = self.nslots(L + 1)
         nsl_ab = self.nslots(nab)
         E("")
-        E("long long g_next = si_g3_next_group(A.counter, lane);")
-        self.open("for (;;)")
-        E("const long long grp = g_next;")
-        E("if (grp >= A.ngroups) break;")
-        E("const int g_raw = si_g3_fetch_group(A.counter, lane);   // consumed only at the end of the group")
+        E("// static round-robin over the warps of a one-wave grid (see gen3c2e.py)")
+        self.open("for (long long grp = g_first; grp < A.ngroups; grp += g_stride)")
         E("// group -> (pair group, charge split): the charges are divided over A.nsplit tuples per pair, each")
         E("// writing its partial matrix slice; the slices are summed in a fixed order afterwards")
         E("const int pg = (int)(grp / A.nsplit), sp = (int)(grp - (long long)pg * A.nsplit);")
@@ -365,13 +362,12 @@ class CoulGen:
         self.close()
         self.close()
         self.sync()
-        E("g_next = si_g3_bcast_group(g_raw);")
-        self.close()  # for(;;)
+        self.close()  # groups
         self.close()  # function
         E("")
         E(f"SI_G3_GLOBAL({self.MB}) void gc_kernel_{name}(GCArgs A) {{")
         E("    SI_G3_KERNEL_PROLOGUE")
-        E(f"    gc_body_{name}(A, g3_lane, g3_smem + (size_t)g3_warp * {self.WSZ * TPW});")
+        E(f"    gc_body_{name}(A, g3_lane, g3_smem + (size_t)g3_warp * {self.WSZ * TPW}, g3_first, g3_stride);")
         E("}")
         E("")
         return "\n".join(self.lines)
@@ -410,9 +406,10 @@ def write_sources(outdir, lmax=4, nparts=4):
         for c in cl:
             g = gens[c]
             cid = c[0] * 10 + c[1]
-            src.append(f"        case {cid}: {{ static bool once = false; if (!once) {{ cudaFuncSetAttribute(gc_kernel_{g.name}, "
-                       f"cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); once = true; }} "
-                       f"gc_kernel_{g.name}<<<grid, block, smem, s>>>(A); return 0; }}")
+            src.append(f"        case {cid}: {{ static int occ = 0; if (!occ) {{ cudaFuncSetAttribute(gc_kernel_{g.name}, "
+                       f"cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); "
+                       f"cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gc_kernel_{g.name}, block, smem); if (occ < 1) occ = 1; }} "
+                       f"gc_kernel_{g.name}<<<si_g3_grid(grid, occ), block, smem, s>>>(A); return 0; }}")
             table.append((cid, pi, g.EPT, g.TPW, g.WSZ))
         src.append("        default: return 1;")
         src.append("    }")
@@ -451,7 +448,7 @@ def write_emu_source(path, classes):
     src = ["#define SI_G3_HOST_EMU 1", HEADER.replace("../si_g3.h", "../../sympleints_b200/csrc/si_g3.h")]
     for c in classes:
         src.append(CoulGen(*c).generate())
-    src.append("struct GCEmuClass { int id, ept, tpw, wsz; void (*body)(const GCArgs&, int, double*); };")
+    src.append("struct GCEmuClass { int id, ept, tpw, wsz; void (*body)(const GCArgs&, int, double*, long long, long long); };")
     src.append("static const GCEmuClass gc_emu_classes[] = {")
     for c in classes:
         g = CoulGen(*c)

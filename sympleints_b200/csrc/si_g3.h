@@ -115,7 +115,8 @@ struct SiG3CheckedW {
 #define SI_G3_KERNEL_PROLOGUE                                   \
     extern thread_local double* si_g3_emu_smem;                 \
     double* g3_smem = si_g3_emu_smem;                           \
-    const int g3_lane = si_g3_emu_lane, g3_warp = 0;
+    const int g3_lane = si_g3_emu_lane, g3_warp = 0;           \
+    const long long g3_first = 0, g3_stride = 1;
 static inline void si_g3_syncwarp() { si_g3_emu_warp->bar->arrive_and_wait(); }
 static inline double si_g3_rsqrt(double x) { return 1.0 / sqrt(x); }
 static inline long long si_g3_next_group(int* counter, int lane) {
@@ -156,8 +157,17 @@ static inline int si_g3_warp_max(int v) {
 #define SI_G3_GLOBAL(mb) __global__ __launch_bounds__(128, mb)
 #define SI_G3_KERNEL_PROLOGUE              \
     extern __shared__ double g3_smem[];    \
-    const int g3_lane = threadIdx.x & 31, g3_warp = threadIdx.x >> 5;
+    const int g3_lane = threadIdx.x & 31, g3_warp = threadIdx.x >> 5;                         \
+    const long long g3_first = (long long)blockIdx.x * (blockDim.x >> 5) + g3_warp,            \
+                    g3_stride = (long long)gridDim.x * (blockDim.x >> 5);
 __device__ __forceinline__ void si_g3_syncwarp() { __syncwarp(); }
+// one-wave grid: at most `occ` resident blocks per SM (the grid passed in is already capped at 4 per SM)
+static inline int si_g3_grid(int grid, int occ) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return grid < sms * occ ? grid : sms * occ;
+}
 __device__ __forceinline__ double si_g3_rsqrt(double x) { return rsqrt(x); }
 __device__ __forceinline__ long long si_g3_next_group(int* counter, int lane) {
     int v = 0;
@@ -165,8 +175,11 @@ __device__ __forceinline__ long long si_g3_next_group(int* counter, int lane) {
     return (long long)__shfl_sync(0xffffffffu, v, 0);
 }
 __device__ __forceinline__ int si_g3_fetch_group(int* counter, int lane) {
+    // Inline PTX on purpose: for atomicAdd() nvcc emits its warp-aggregation pattern (leader election,
+    // ATOMG, then a SHFL that broadcasts the result at once), i.e. the warp waits for the round trip here
+    // and the prefetch is lost.  The raw instruction leaves the result untouched until the caller needs it.
     int v = 0;
-    if (lane == 0) v = atomicAdd(counter, 1);
+    if (lane == 0) asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(v) : "l"(counter) : "memory");
     return v;
 }
 __device__ __forceinline__ long long si_g3_bcast_group(int v) {

@@ -99,7 +99,7 @@ extern "C" int gcemu_eval(int La, int Lb, int npairs, const int* Ka, const doubl
             si_g3_emu_warp = &warp;
             si_g3_emu_lane = lane;
             si_g3_emu_smem = smem.data();
-            cls->body(args, lane, smem.data());
+            cls->body(args, lane, smem.data(), 0, 1);
         });
     for (auto& t : th) t.join();
     for (int sp = 1; sp < nsplit; ++sp)
