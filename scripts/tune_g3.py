@@ -3,7 +3,7 @@ per-class timing on the GPU box (SI_G3_PROFILE=1), and merge the timings into co
 import json, os, subprocess, sys, shutil
 from pathlib import Path
 REPO = Path(__file__).resolve().parent.parent
-VARIANTS = [(sh, mb, 36) for sh in (-1, 0, 1) for mb in (2, 3, 4)]
+VARIANTS = [(sh, mb, 36) for sh in (-2, -1, 0, 1) for mb in (2, 3, 4)]
 if os.environ.get('TUNE_ONLY_EXTRA'):
     VARIANTS = [(sh, 2, 60) for sh in (0, 1)]
 
@@ -19,7 +19,7 @@ def build():
 def merge(logdir):
     sys.path.insert(0, str(REPO))
     best = {}
-    allv = [(sh, mb, 36) for sh in (-1, 0, 1) for mb in (2, 3, 4)]
+    allv = VARIANTS
     for sh, mb, yr in allv:
         f = Path(logdir) / f"tune_sh{sh}_mb{mb}_y{yr}.log"
         if not f.exists() and yr == 36:
