@@ -1201,7 +1201,12 @@ static void g3_fill_args(G3Args& ga, si_context* c, const BasisDev& orb, const B
 }
 static bool g3_config(const si_context* c, const int* g3, long long ngroups, int* grid, int* block, size_t* smem) {
     const size_t per_warp = (size_t)g3[4] * g3[3] * sizeof(double);  // WSZ * TPW
-    int nw = (int)std::min<size_t>(4, (size_t)c->max_smem / per_warp);
+    static int wpb = -1;   // warps per block (the kernels are compiled for up to 4)
+    if (wpb < 0) {
+        const char* e = getenv("SI_G3_WARPS_PER_BLOCK");
+        wpb = e ? std::max(1, std::min(4, atoi(e))) : 4;
+    }
+    int nw = (int)std::min<size_t>((size_t)wpb, (size_t)c->max_smem / per_warp);
     if (nw < 1) return false;
     *block = nw * 32;
     *smem = per_warp * nw;
@@ -1210,7 +1215,7 @@ static bool g3_config(const si_context* c, const int* g3, long long ngroups, int
         const char* e = getenv("SI_G3_GRID_PER_SM");
         per_sm = e ? std::max(1, atoi(e)) : 4;   // persistent blocks: at most 4 x 4 warps are resident per SM
     }
-    *grid = (int)std::max<long long>(1, std::min<long long>((ngroups + nw - 1) / nw, (long long)c->sm_count * per_sm));
+    *grid = (int)std::max<long long>(1, std::min<long long>((ngroups + nw - 1) / nw, (long long)c->sm_count * per_sm * (4 / nw)));
     return true;
 }
 
