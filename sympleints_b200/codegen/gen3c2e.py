@@ -449,16 +449,13 @@ class ClassGen:
                   f"const int yc_{s} = min(max(q + EPT * {s}, {off(La)}), {self.NA - 1}) - {off(La)};")
         E("")
         # ---- work loop over tuple groups
-        E("// Work is handed out in chunks of A.chunk consecutive groups per atomic (one global counter would")
-        E("// otherwise serialise ~10^7 same-address atomics per step); the next chunk index is fetched one")
-        E("// chunk ahead so that the atomic's round trip is hidden.")
+        E("// Work is handed out through one atomic counter per launch, one group per request; the next index is")
+        E("// requested after the primitive phase and consumed (broadcast) at the end of the group.")
         E("long long ch_next = si_g3_next_group(A.counter, lane);")
         self.open("for (;;)")
-        E("const long long ch = ch_next;")
-        E("if (ch * A.chunk >= A.ngroups) break;")
-        E("int ch_raw = 0;")
-        E("const long long g_end = min((ch + 1) * (long long)A.chunk, A.ngroups);")
-        self.open("for (long long grp = ch * A.chunk; grp < g_end; ++grp)")
+        E("const long long grp = ch_next;")
+        E("if (grp >= A.ngroups) break;")
+        self.open("")
         E("// group -> (pair, first aux of the group); tuples beyond the run end recompute the last valid one")
         E("const int ip = (int)(grp / A.groups_per_pair);")
         E("const int gi = (int)(grp - (long long)ip * A.groups_per_pair);")
@@ -500,7 +497,7 @@ class ClassGen:
         E("// Fetch the next chunk index now: raw atomic result of lane 0, consumed (broadcast) at the chunk end, so")
         E("// its round trip overlaps the contracted phase.  (Issued earlier, the result register gets spilled, and")
         E("// the spill store waits for the atomic.)")
-        E("if (grp + 1 >= g_end) ch_raw = si_g3_fetch_group(A.counter, lane);")
+        E("const int ch_raw = si_g3_fetch_group(A.counter, lane);")
         if self.YREG:
             self.sync("last primitive's readers of the overlaid arrays are done")
             for m in range(self.nm):
@@ -515,8 +512,8 @@ class ClassGen:
         else:
             E("if (valid && q == 0) A.od.out[0] = W[0];")
         self.sync()
-        self.close()  # groups of the chunk
         E("ch_next = si_g3_bcast_group(ch_raw);")
+        self.close()  # group scope
         self.close()  # for(;;)
         self.close()  # function
         E("")
