@@ -215,6 +215,10 @@ class ClassGen:
         o += 6 + (L + 1)
         if o % 2:
             o += 1
+        # per-item metadata of the HRR stage (packed ints, two per double), filled once per kernel
+        self.HM_OFF = o
+        if self.Lb > 0:
+            o += (self.nca * self.nm + 1) // 2
         # Y[m][a'] persistent over primitives: the leaves of the aux recurrence are folded straight
         # into the spherical components (C2S on c), so no Cartesian [a0|c] block is ever stored
         self.YS = self.n_ap + ypad                 # stride between m rows of Y
@@ -448,6 +452,14 @@ class ClassGen:
                 E(f"const bool yv_{s} = (q + EPT * {s} >= {off(La)}) && (q + EPT * {s} < {self.NA}); "
                   f"const int yc_{s} = min(max(q + EPT * {s}, {off(La)}), {self.NA - 1}) - {off(La)};")
         E("")
+        if Lb > 0:
+            nit_h = self.nca * self.nm
+            E("// HRR work items (target a component, m), a fastest: Y base address | row of a << 13 | Z address << 16")
+            self.open(f"for (int item = q; item < {nit_h}; item += EPT)")
+            E(f"const int m = item / {self.nca}, ai = item - m * {self.nca};")
+            E(f"((int*)&W[{self.HM_OFF}])[item] = ({self.Y_OFF} + m * {self.YS} + ai) | (si_g3_tri_row(ai) << 13) | (({self.Z_OFF} + ai * {self.nsb * self.nm} + m) << 16);")
+            self.close()
+            self.sync()
         # ---- work loop over tuple groups
         E("// Work is handed out through one atomic counter per launch, one group per request; the next index is")
         E("// requested after the primitive phase and consumed (broadcast) at the end of the group.")
@@ -776,9 +788,8 @@ class ClassGen:
 
         targets = [node([0, 0, 0], list(b)) for b in cart_order(Lb)]
         self.open(f"for (int item = q; item < {nit}; item += EPT)")
-        E(f"const int m = item / {nca}, ai = item - m * {nca};   // a fastest: near-consecutive shared-memory addresses")
-        E("const int ia_ = si_g3_tri_row(ai);   // row of the target a (l = La - ia_)")
-        E(f"const int yb = {self.Y_OFF} + m * {self.YS} + ai;")
+        E(f"const int hm_ = ((const int*)&W[{self.HM_OFF}])[item];   // items (m, a), a fastest: near-consecutive addresses")
+        E("const int yb = hm_ & 0x1FFF, ia_ = (hm_ >> 13) & 7, zb = hm_ >> 16;   // ia_: row of the target a (l = La - ia_)")
         for ik in range(Lb + 1):
             E(f"const int yb{ik} = yb + ia_ * {ik};")
         # inputs: idx(a+k) - idx-base: off(La+|k|)-off(La) + row(ik) + nz_k + ia*ik   (+ ai)
@@ -803,7 +814,7 @@ class ClassGen:
                 expr = f"{lit(coef)} * {targets[j]}" if expr is None else f"fma({lit(coef)}, {targets[j]}, {expr})"
             E(f"const double zb{jb} = {expr};")
         for jb in range(nsb):
-            E(f"W[{self.Z_OFF + jb * nm} + ai * {nsb * nm} + m] = zb{jb};")
+            E(f"W[zb + {jb * nm}] = zb{jb};")
         self.close()
 
     # ---- C2S(a) + global store --------------------------------------------------------------
