@@ -6,9 +6,3 @@ for f in $V/lib_sh*_mb*.so; do
   SYMPLEINTS_B200_LIB=$PWD/$f SI_GC_PROFILE=1 python scripts/coul_bench.py 2 > /dev/null 2> gpurun_out/tunegc_$tag.log
   echo $tag $(grep -c GCPROF gpurun_out/tunegc_$tag.log)
 done
-export SYMPLEINTS_B200_LIB=$PWD/$V/lib_sh-1_mb2.so
-echo "default split"; python scripts/coul_bench.py 3
-echo "no split"; SI_GC_MAX_SPLIT=1 python scripts/coul_bench.py 3
-echo "warps/SM 4"; SI_GC_WARPS_PER_SM=4 python scripts/coul_bench.py 3
-echo "warps/SM 16"; SI_GC_WARPS_PER_SM=16 python scripts/coul_bench.py 3
-echo "warps/SM 16 maxsplit 32"; SI_GC_WARPS_PER_SM=16 SI_GC_MAX_SPLIT=32 python scripts/coul_bench.py 3
