@@ -79,6 +79,8 @@ class CoulGen:
                     continue
                 self.V_OFF[(n, jn)] = o
                 o += ncart(n)
+        self.SX_OFF = o          # (P - C), two buffers by charge parity (lanes whose direction is not uniform)
+        o += 6
         end1 = o
         # (2) after the charge loop, over the dead recursion arrays: Rbar (flat over shells 0..L) and the
         # E tables [d][i][j][t]
@@ -199,28 +201,45 @@ class CoulGen:
         for s in range(nsl_b):
             E(f"const int jb_{s} = min(q + EPT * {s}, {L}); double mp_{s} = 1.0; "
               f"{{ double bb = -2.0 * p; int e_ = jb_{s}; for (int i_ = 0; i_ < 4; ++i_) {{ if (e_ & 1) mp_{s} *= bb; bb *= bb; e_ >>= 1; }} }}")
+        for s in range(nsl_b):
+            E(f"const double xp_{s} = A.boys.xlarge_pref[jb_{s}];   // asymptotic Boys prefactor of this lane's order")
         # accumulators over the charges
         E("double yr_0 = 0.0;")
         for n in range(1, L + 1):
             E("double " + ", ".join(f"yr_{n}_{s} = 0.0" for s in range(nsl_v[n])) + ";")
+        # which (shell, slot) have lanes of different recursion directions?
+        mixed = {}
+        for n in range(1, L + 1):
+            for s in range(nsl_v[n]):
+                ds = {vm[n][min(q_ + EPT * s, ncart(n) - 1)][0] for q_ in range(EPT)}
+                mixed[(n, s)] = None if len(ds) > 1 else ds.pop()
+        need_sx = any(v is None for v in mixed.values())
+        E("// charges are packed (x, y, z, q); the next record is loaded one iteration ahead")
+        E("double cn0 = A.c4[4 * c0], cn1 = A.c4[4 * c0 + 1], cn2 = A.c4[4 * c0 + 2], cn3 = A.c4[4 * c0 + 3];")
         self.open("for (int ic = c0; ic < c1; ++ic)")
-        E("const double qc = A.cq[ic];")
-        E("const double X0 = P0 - A.cxyz[3 * ic], X1 = P1 - A.cxyz[3 * ic + 1], X2 = P2 - A.cxyz[3 * ic + 2];")
+        E("const double X0 = P0 - cn0, X1 = P1 - cn1, X2 = P2 - cn2, qc = cn3;")
+        E("{ const double* cc_ = A.c4 + 4 * min(ic + 1, c1 - 1); cn0 = cc_[0]; cn1 = cc_[1]; cn2 = cc_[2]; cn3 = cc_[3]; }")
         E("const double T = p * (X0 * X0 + X1 * X1 + X2 * X2);")
         # base values: V(0, j) = qc (-2p)^j F_j(T)
         for s in range(nsl_b):
-            E(f"const double bv_{s} = qc * mp_{s} * si_boys_fast(A.boys, jb_{s}, T);")
+            E(f"const double bv_{s} = qc * mp_{s} * si_boys_fast_pref(A.boys, jb_{s}, T, xp_{s});")
         E("yr_0 += bv_0;   // lane q == 0 holds j = 0")
         if L >= 1:
             for s in range(nsl_b):
                 E(f"W[{self.V_OFF[(0, 0)]} + jb_{s}] = bv_{s};")
+            if need_sx:
+                E(f"const int sx_ = {self.SX_OFF} + 3 * (ic & 1);")
+                E("if (q == 0) { W[sx_] = X0; W[sx_ + 1] = X1; W[sx_ + 2] = X2; }")
             self.sync()
         for n in range(1, L + 1):
             njn = L - n + 1          # orders jn = 0..njn-1 of this shell
             self.open("")
             for s in range(nsl_v[n]):
                 E(f"const int m{s}_ = vm_{n}_{s}; const int d{s}_ = m{s}_ & 3; const int k1_{s} = (m{s}_ >> 8) & 0xFF; const int k2_{s} = (m{s}_ >> 16) & 0xFF;")
-                E(f"const double cp{s}_ = d{s}_ == 0 ? X0 : (d{s}_ == 1 ? X1 : X2);")
+                if mixed[(n, s)] is None:
+                    E(f"const double cp{s}_ = W[sx_ + d{s}_];   // lanes of this slot differ in direction")
+                else:
+                    E(f"const double cp{s}_ = X{mixed[(n, s)]};   // every lane of this slot recurs along the same direction")
                 for jn in range(1, njn + 1):
                     E(f"const double u{s}_{jn} = W[{self.V_OFF[(n - 1, jn)]} + k1_{s}];")
                     if n >= 2:

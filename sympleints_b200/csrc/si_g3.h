@@ -69,8 +69,7 @@ struct GCArgs {
     const SiPairItem* pairs;
     const double* ppair;   // as in G3Args
     int npairs;
-    const double* cxyz;    // ncharge x 3
-    const double* cq;      // ncharge
+    const double* c4;      // ncharge packed records (x, y, z, q)
     int ncharge;
     int nsplit;            // charge ranges per pair: split 0 writes od.out, split sp >= 1 slice sp-1 of `part`
     double* part;          // (nsplit_max - 1) zero-initialised nbf x nbf slices, summed into od.out afterwards

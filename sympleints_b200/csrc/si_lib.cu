@@ -1011,8 +1011,8 @@ __global__ void k_sum_slices(double* out, const double* part, long long n, int n
 
 // Nuclear attraction through the generated McMurchie-Davidson kernels (codegen/gencoul.py): one tuple per
 // shell pair, all charges inside; every class on its own stream so that the tails overlap.
-static int run_coul_generated(si_context* c, const si_basis* cb, int normalize, int ncharge, const double* d_cxyz,
-                              const double* d_q, double* out_dev, cudaStream_t user) {
+static int run_coul_generated(si_context* c, const si_basis* cb, int normalize, int ncharge, const double* d_c4,
+                              double* out_dev, cudaStream_t user) {
     si_basis* b = const_cast<si_basis*>(cb);
     int rc = build_pair_classes(b);
     if (rc) return rc;
@@ -1053,7 +1053,7 @@ static int run_coul_generated(si_context* c, const si_basis* cb, int normalize, 
         double* base = nullptr;
         rc = ctx_scratch(c, (size_t)4 * ncharge + (size_t)(top_split - 1) * nbf * nbf, user, &base);
         if (rc) return rc;
-        if (base + 0 != d_cxyz) {
+        if (base + 0 != d_c4) {
             g_last_error = "coul scratch moved";
             return SI_ERR_INTERNAL;
         }
@@ -1082,8 +1082,7 @@ static int run_coul_generated(si_context* c, const si_basis* cb, int normalize, 
         ga.pairs = pc.d_items;
         ga.ppair = b->full.d_ppair[normalize == SI_NORM_PGTO ? 1 : 0];
         ga.npairs = pc.n;
-        ga.cxyz = d_cxyz;
-        ga.cq = d_q;
+        ga.c4 = d_c4;
         ga.ncharge = ncharge;
         ga.nsplit = nsplits[ci++];
         ga.ngroups = (long long)((pc.n + gc[3] - 1) / gc[3]) * ga.nsplit;
@@ -1136,14 +1135,23 @@ int si_coul(si_context* c, const si_basis* b, int sph, int normalize, int ncharg
     double* dx = nullptr;
     int rc = ctx_scratch(c, (size_t)4 * ncharge + (generated ? (size_t)(SI_GC_MAX_SPLIT - 1) * nbf * nbf : 0), s, &dx);
     if (rc) return rc;
+    if (generated) {
+        // packed records (x, y, z, q): one 32-byte sector per charge
+        std::vector<double> c4((size_t)4 * ncharge);
+        for (int i = 0; i < ncharge; ++i) {
+            c4[4 * (size_t)i] = xyz[3 * (size_t)i];
+            c4[4 * (size_t)i + 1] = xyz[3 * (size_t)i + 1];
+            c4[4 * (size_t)i + 2] = xyz[3 * (size_t)i + 2];
+            c4[4 * (size_t)i + 3] = q[i];
+        }
+        SI_CUDA(cudaMemcpyAsync(dx, c4.data(), c4.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        SI_CUDA(cudaStreamSynchronize(s));   // c4 is a temporary (pageable copies are staged, but be explicit)
+        return run_coul_generated(c, b, normalize, ncharge, dx, out_dev, s);
+    }
     double* dq = dx + (size_t)3 * ncharge;
     SI_CUDA(cudaMemcpyAsync(dx, xyz, (size_t)ncharge * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
     SI_CUDA(cudaMemcpyAsync(dq, q, (size_t)ncharge * sizeof(double), cudaMemcpyHostToDevice, s));
-    if (generated)
-        rc = run_coul_generated(c, b, normalize, ncharge, dx, dq, out_dev, s);
-    else
-        rc = run_two_index(c, b, SI_COUL, sph, normalize, nullptr, ncharge, dx, dq, out_dev, s);
-    return rc;
+    return run_two_index(c, b, SI_COUL, sph, normalize, nullptr, ncharge, dx, dq, out_dev, s);
 }
 
 // ---- generated class-specialised 3c2e kernels (codegen/gen3c2e.py) ----------------------------

@@ -196,23 +196,29 @@ SI_HD double si_boys(const SiBoys& B, int n, double x) {
 
 // Same algorithm, cheaper evaluation for the generated kernels: Horner form of the 6-term Taylor sum and
 // x^(-n-1/2) = sqrt(1/x) (1/x)^n by binary exponentiation instead of pow() (differences ~1e-16 relative).
-SI_HD double si_boys_fast(const SiBoys& B, int n, double x) {
-    if (x < 30.0) {
-        // (x == 0 gives ind0 = 0, mdx = 0 and the sum reduces to the tabulated F_n(0) exactly)
-        const int ind0 = (int)(x * 10.0);
-        const double mdx = ind0 * 0.1 - x;
-        const double* t = B.tableT + ind0 * B.nrows + n;
-        const double t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3], t4 = t[4], t5 = t[5];
-        double r = t5 * (1.0 / 120.0);
-        r = fma(r, mdx, t4 * (1.0 / 24.0));
-        r = fma(r, mdx, t3 * (1.0 / 6.0));
-        r = fma(r, mdx, t2 * 0.5);
-        r = fma(r, mdx, t1);
-        r = fma(r, mdx, t0);
-        return r;
-    }
-    const double inv = 1.0 / x;
-    double acc = sqrt(inv), b = inv;
+SI_HD double si_boys_taylor(const SiBoys& B, int n, double x) {
+    // (x == 0 gives ind0 = 0, mdx = 0 and the sum reduces to the tabulated F_n(0) exactly)
+    const int ind0 = (int)(x * 10.0);
+    const double mdx = ind0 * 0.1 - x;
+    const double* t = B.tableT + ind0 * B.nrows + n;
+    const double t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3], t4 = t[4], t5 = t[5];
+    double r = t5 * (1.0 / 120.0);
+    r = fma(r, mdx, t4 * (1.0 / 24.0));
+    r = fma(r, mdx, t3 * (1.0 / 6.0));
+    r = fma(r, mdx, t2 * 0.5);
+    r = fma(r, mdx, t1);
+    r = fma(r, mdx, t0);
+    return r;
+}
+// x^(-n-1/2) from ONE reciprocal square root (a division and a square root cost ~3x as much; point charges
+// far from the pair make the asymptotic branch the common one in the nuclear-attraction kernels)
+SI_HD double si_boys_xpow(int n, double x) {
+#if defined(__CUDA_ARCH__)
+    const double rs = rsqrt(x);
+#else
+    const double rs = 1.0 / sqrt(x);
+#endif
+    double acc = rs, b = rs * rs;
     int e = n;
 #pragma unroll
     for (int it = 0; it < 5; ++it) {
@@ -220,7 +226,16 @@ SI_HD double si_boys_fast(const SiBoys& B, int n, double x) {
         b *= b;
         e >>= 1;
     }
-    return B.xlarge_pref[n] * acc;
+    return acc;
+}
+SI_HD double si_boys_fast(const SiBoys& B, int n, double x) {
+    if (x < 30.0) return si_boys_taylor(B, n, x);
+    return B.xlarge_pref[n] * si_boys_xpow(n, x);
+}
+// pref_n = B.xlarge_pref[n], for callers with a fixed order per lane (kept in a register)
+SI_HD double si_boys_fast_pref(const SiBoys& B, int n, double x, double pref_n) {
+    if (x < 30.0) return si_boys_taylor(B, n, x);
+    return pref_n * si_boys_xpow(n, x);
 }
 
 // ---- dynamic scalar table fill ----------------------------------------------

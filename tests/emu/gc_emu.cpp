@@ -68,8 +68,12 @@ extern "C" int gcemu_eval(int La, int Lb, int npairs, const int* Ka, const doubl
     args.pairs = items.data();
     args.ppair = pp.data();
     args.npairs = npairs;
-    args.cxyz = cxyz;
-    args.cq = cq;
+    std::vector<double> c4((size_t)4 * ncharge);
+    for (int i = 0; i < ncharge; ++i) {
+        for (int d = 0; d < 3; ++d) c4[4 * i + d] = cxyz[3 * i + d];
+        c4[4 * i + 3] = cq[i];
+    }
+    args.c4 = c4.data();
     args.ncharge = ncharge;
     args.nsplit = nsplit;
     args.ngroups = (long long)((npairs + cls->tpw - 1) / cls->tpw) * nsplit;
