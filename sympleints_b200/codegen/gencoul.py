@@ -221,8 +221,17 @@ class CoulGen:
         E("{ const double* cc_ = A.c4 + 4 * min(ic + 1, c1 - 1); cn0 = cc_[0]; cn1 = cc_[1]; cn2 = cc_[2]; cn3 = cc_[3]; }")
         E("const double T = p * (X0 * X0 + X1 * X1 + X2 * X2);")
         # base values: V(0, j) = qc (-2p)^j F_j(T)
+        # (one reciprocal square root per charge for all orders of the lane in the asymptotic branch)
+        E("double " + ", ".join(f"bv_{s}" for s in range(nsl_b)) + ";")
+        self.open("if (T < 30.0)")
         for s in range(nsl_b):
-            E(f"const double bv_{s} = qc * mp_{s} * si_boys_fast_pref(A.boys, jb_{s}, T, xp_{s});")
+            E(f"bv_{s} = qc * mp_{s} * si_boys_taylor(A.boys, jb_{s}, T);")
+        self.close()
+        self.open("else")
+        E("const double rs_ = si_rsqrt(T);")
+        for s in range(nsl_b):
+            E(f"bv_{s} = qc * mp_{s} * xp_{s} * si_boys_xpow_rs(jb_{s}, rs_);")
+        self.close()
         E("yr_0 += bv_0;   // lane q == 0 holds j = 0")
         if L >= 1:
             for s in range(nsl_b):

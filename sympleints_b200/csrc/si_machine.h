@@ -212,12 +212,27 @@ SI_HD double si_boys_taylor(const SiBoys& B, int n, double x) {
 }
 // x^(-n-1/2) from ONE reciprocal square root (a division and a square root cost ~3x as much; point charges
 // far from the pair make the asymptotic branch the common one in the nuclear-attraction kernels)
-SI_HD double si_boys_xpow(int n, double x) {
+SI_HD double si_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)
-    const double rs = rsqrt(x);
+    return rsqrt(x);
 #else
-    const double rs = 1.0 / sqrt(x);
+    return 1.0 / sqrt(x);
 #endif
+}
+// rs^(2n+1) for rs = x^(-1/2), by binary powering (n < 32)
+SI_HD double si_boys_xpow_rs(int n, double rs) {
+    double acc = rs, b = rs * rs;
+    int e = n;
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+        if (e & 1) acc *= b;
+        b *= b;
+        e >>= 1;
+    }
+    return acc;
+}
+SI_HD double si_boys_xpow(int n, double x) {
+    const double rs = si_rsqrt(x);
     double acc = rs, b = rs * rs;
     int e = n;
 #pragma unroll
