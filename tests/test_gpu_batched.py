@@ -92,6 +92,21 @@ def test_nuclear_attraction_with_point_charges(engine, small):
             assert np.abs(g[blk] - o[blk]).max() <= tol, (i, j)
 
 
+def test_nuclear_attraction_charge_split(engine, small):
+    """Many charges: the generated kernels split them over several tuples per shell pair (partial matrices
+    summed by k_sum_slices); the result must agree with the sum of unsplit evaluations of 25-charge chunks."""
+    shells, sites, _, ob, _ = small
+    xyz, q = synthetic.point_charges(sites, n=200, seed=9)
+    g = engine.coul(ob, xyz, q).cpu().numpy()
+    parts = sum(engine.coul(ob, xyz[i:i + 25], q[i:i + 25]).cpu().numpy() for i in range(0, 200, 25))
+    assert np.abs(g - parts).max() <= 1e-13 * np.abs(g).max()
+    assert np.abs(g - g.T).max() <= 1e-15 * np.abs(g).max()
+    # a single charge
+    g1 = engine.coul(ob, xyz[:1], q[:1]).cpu().numpy()
+    o1 = q[0] * oracle_matrix("coul", shells, R=xyz[0])[0]
+    assert np.abs(g1 - o1).max() <= 1e-14 + 1e-12 * np.abs(o1).max()
+
+
 @pytest.mark.parametrize("sph,normalize", [(True, "pgto"), (False, "cgto"), (True, "none")])
 def test_nuclear_attraction_other_variants(engine, small, sph, normalize):
     """pgto goes through the generated kernels, Cartesian / un-normalised output through the stage machine."""
