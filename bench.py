@@ -237,6 +237,33 @@ def config_dict(shells, aux, work, world, note):
     }
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Run this rank on the CPU cores local to its GPU (sysfs local_cpulist of the PCI device), so that the
+    pinned host buffer of the end-to-end leg is allocated on the NUMA node the GPU's PCIe link hangs off.
+    (No effect on the single-node-slice boxes of this pool, where all 16 cores are local; the end-to-end
+    time there varies 0.68-0.97 s between boxes and runs.)  SI_BENCH_NO_AFFINITY=1 disables it."""
+    if os.environ.get("SI_BENCH_NO_AFFINITY") == "1":
+        return None
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        txt = open(path).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return txt
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -247,6 +274,7 @@ def run_ours(args, rank, world, local_rank):
     from sympleints_b200.shells import shells_to_soa
 
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank)
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
     os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug_%h_%p.log")
@@ -331,7 +359,7 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": work["integrals"] / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(mywork["bytes"]), "steps": n_e2e, "s_per_step": float(dt.item()),
-               "pinned_host_buffer": pinned,
+               "pinned_host_buffer": pinned, "cpu_affinity": numa,
                "path": "si_basis_create (H2D) + si_int3c2e_h (row-chunked compute overlapped with contiguous cudaMemcpyAsync D2H)"}
         del host
 
