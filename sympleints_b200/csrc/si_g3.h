@@ -58,7 +58,7 @@ struct G3Args {
     int col_begin;
     int groups_per_pair;  // ceil(naux_c / tuples-per-warp)
     long long ngroups;    // npairs * groups_per_pair
-    int chunk;            // groups handed out per atomic
+    int chunk;            // unused (the kernels request one group per atomic); kept for ABI stability of the struct
     OutDesc od;
     int* counter;
     SiBoys boys;
