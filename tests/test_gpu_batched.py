@@ -199,3 +199,45 @@ def test_host_path_chunking_is_exact(engine, small, monkeypatch):
         assert np.array_equal(engine.int3c2e_host(ob, ab, layout="full"), Tf), nbytes
         assert np.array_equal(engine.int3c2e_host(ob, ab, shell_range=(3, 40), layout="packed"),
                               engine.int3c2e(ob, ab, shell_range=(3, 40), layout="packed").cpu().numpy()), nbytes
+
+
+def test_edge_cases_single_shell_and_reversed_order(engine):
+    """Smallest inputs (one shell, one primitive, one charge, one aux shell) and a shell list in descending
+    angular momentum (every off-diagonal pair is a "swapped" one, L(i) < L(j) never holds for i > j ... and
+    the reverse list makes it hold for all)."""
+    from sympleints_b200.shells import Shell
+
+    g = Shell(4, [0.1, -0.2, 0.3], [1.0], [0.8])
+    h = Shell(5, [0.4, 0.1, -0.3], [1.0], [1.1])
+    bg, bh = engine.basis([g]), engine.basis([h])
+    S = engine.int1e("ovlp", bg).cpu().numpy().reshape(9, 9)
+    assert np.abs(S - np.eye(9)).max() <= 1e-13            # cgto-normalised spherical g shell
+    V = engine.coul(bg, np.array([[0.5, 0.5, -0.5]]), np.array([-2.0])).cpu().numpy()
+    oV = -2.0 * oracle_matrix("coul", [g], R=np.array([0.5, 0.5, -0.5]))[0]
+    assert np.abs(V - oV).max() <= 1e-14 + 1e-12 * np.abs(oV).max()
+    M = engine.int2c2e(bh).cpu().numpy()
+    oM = oracle_matrix("2c2e", [h])[0]
+    assert np.abs(M - oM).max() <= 1e-14 + 1e-12 * np.abs(oM).max()
+    T = engine.int3c2e(bg, bh, layout="full").cpu().numpy()
+    oT = _oracle_3c_block(g, g, h).reshape(9, 9, 11)
+    assert np.abs(T - oT).max() <= 1e-14 + 1e-12 * np.abs(oT).max()
+    Tp = engine.int3c2e(bg, bh, layout="packed").cpu().numpy()
+    assert np.array_equal(Tp.reshape(9, 9, 11), T)
+    # mixed list in both orders: the matrices are permutations of each other
+    rng = np.random.default_rng(11)
+    shells = [Shell(L, rng.uniform(-1, 1, 3), rng.uniform(0.2, 1, k), 10 ** rng.uniform(-0.5, 1, k))
+              for L, k in ((0, 3), (1, 2), (2, 1), (3, 1), (4, 1))]
+    rev = shells[::-1]
+    a = engine.int1e("kin", engine.basis(shells)).cpu().numpy().reshape(25, 25)
+    b = engine.int1e("kin", engine.basis(rev)).cpu().numpy().reshape(25, 25)
+    off_a = np.concatenate([[0], np.cumsum(_sizes(shells, True))])
+    off_b = np.concatenate([[0], np.cumsum(_sizes(rev, True))])
+    perm = np.concatenate([np.arange(off_b[len(rev) - 1 - i], off_b[len(rev) - i]) for i in range(len(shells))])
+    assert np.abs(a - b[np.ix_(perm, perm)]).max() <= 1e-13 * np.abs(a).max()
+    aux = [h, Shell(2, [0.0, 0.3, 0.1], [1.0], [0.6])]
+    ta = engine.int3c2e(engine.basis(shells), engine.basis(aux), layout="full").cpu().numpy()
+    tb = engine.int3c2e(engine.basis(rev), engine.basis(aux), layout="full").cpu().numpy()
+    assert np.abs(ta - tb[np.ix_(perm, perm)]).max() <= 1e-13 * np.abs(ta).max()
+    va = engine.coul(engine.basis(shells), np.array([[0.2, 0.1, 0.4], [1.0, -1.0, 0.5]]), np.array([1.0, -0.5])).cpu().numpy()
+    vb = engine.coul(engine.basis(rev), np.array([[0.2, 0.1, 0.4], [1.0, -1.0, 0.5]]), np.array([1.0, -0.5])).cpu().numpy()
+    assert np.abs(va - vb[np.ix_(perm, perm)]).max() <= 1e-13 * np.abs(va).max()
