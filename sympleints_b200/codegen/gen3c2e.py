@@ -190,6 +190,10 @@ class ClassGen:
         self.ind = 1
         self._layout()
 
+    def has_table_variant(self):
+        """Classes with >= 4 tuples per warp also get a kernel that takes its tuples from a host-built table."""
+        return self.TPW >= 4
+
     # ---- shared-memory layout (doubles, per tuple) ------------------------------------
     def amin(self, level):
         return max(0, self.La - (self.Lc - level))
@@ -430,7 +434,10 @@ class ClassGen:
             E(f"__device__ const int g3_df_{name}[{len(vals)}] = {{{', '.join(map(str, vals))}}};")
         E("")
         E(f"// class ({La}{Lb}|{Lc}): EPT={EPT} lanes per tuple, {TPW} tuples per warp, {self.WSZ} doubles of shared memory per tuple")
-        E(f"SI_G3_DEV void g3_body_{name}(const G3Args& A, const int lane, double* wbase) {{")
+        E("// TAB: the group's tuples come from the host-built table A.tuples.  A template parameter, not a run-time")
+        E("// branch: in the default instantiation the pair index stays warp-uniform for the compiler (uniform")
+        E("// registers for the pair record), which is worth 5 % of the step.")
+        E(f"template <bool TAB> SI_G3_DEV void g3_body_{name}(const G3Args& A, const int lane, double* wbase) {{")
         self.ind = 1
         E(f"constexpr int EPT = {EPT}, TPW = {TPW}, WSZ = {self.WSZ};")
         E("const int q = lane % EPT, tl = lane / EPT;")
@@ -468,12 +475,18 @@ class ClassGen:
         E("const long long grp = ch_next;")
         E("if (grp >= A.ngroups) break;")
         self.open("")
-        E("// group -> (pair, first aux of the group); tuples beyond the run end recompute the last valid one")
-        E("const int ip = (int)(grp / A.groups_per_pair);")
+        E("// group -> TPW tuples.  Default: one pair, TPW consecutive aux shells of the class; tuples beyond the run")
+        E("// end recompute the last valid one.  With a host-built tuple table (used when only a few aux shells of")
+        E("// the class are in the range, e.g. one rank's shard of many, so that per-pair packing would leave most")
+        E("// lanes idle) the group's tuples are listed explicitly: (pair, aux) of equal contraction lengths, -1 =")
+        E("// padding (recomputes the group's first tuple).")
+        E("int2 t_ = TAB ? A.tuples[grp * TPW + tl] : int2{0, 0};")
+        E("if (TAB && t_.x < 0) t_ = A.tuples[grp * TPW];")
+        E("const int ip = TAB ? t_.x : (int)(grp / A.groups_per_pair);")
         E("const int gi = (int)(grp - (long long)ip * A.groups_per_pair);")
-        E("int ic = gi * TPW + tl;")
-        E("const bool valid = ic < A.naux_c;")
-        E("if (!valid) ic = A.naux_c - 1;")
+        E("int ic = TAB ? t_.y : gi * TPW + tl;")
+        E("const bool valid = TAB ? (A.tuples[grp * TPW + tl].x >= 0) : (ic < A.naux_c);")
+        E("if (!TAB && !valid) ic = A.naux_c - 1;")
         E("const SiPairItem it = A.pairs[ip];")
         E("const SiAuxItem ai_ = A.auxitems[ic];")
         E("const int sc = ai_.shell; (void)sc;")
@@ -532,8 +545,13 @@ class ClassGen:
         # kernel wrapper
         E(f"SI_G3_GLOBAL({self.MB}) void g3_kernel_{name}(G3Args A) {{")
         E("    SI_G3_KERNEL_PROLOGUE")
-        E(f"    g3_body_{name}(A, g3_lane, g3_smem + (size_t)g3_warp * {self.WSZ * TPW});")
+        E(f"    g3_body_{name}<false>(A, g3_lane, g3_smem + (size_t)g3_warp * {self.WSZ * TPW});")
         E("}")
+        if self.has_table_variant():
+            E(f"SI_G3_GLOBAL({self.MB}) void g3_tkernel_{name}(G3Args A) {{")
+            E("    SI_G3_KERNEL_PROLOGUE")
+            E(f"    g3_body_{name}<true>(A, g3_lane, g3_smem + (size_t)g3_warp * {self.WSZ * TPW});")
+            E("}")
         E("")
         return "\n".join(self.lines)
 
@@ -914,7 +932,10 @@ def write_sources(outdir, lmax=4, lauxmax=5, nparts=15):
         for c in cl:
             g = gens[c]
             cid = c[0] * 100 + c[1] * 10 + c[2]
-            src.append(f"        case {cid}: {{ static bool once = false; if (!once) {{ cudaFuncSetAttribute(g3_kernel_{g.name}, "
+            tk = (f"if (A.tuples) {{ static bool tonce = false; if (!tonce) {{ cudaFuncSetAttribute(g3_tkernel_{g.name}, "
+                  f"cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); tonce = true; }} "
+                  f"g3_tkernel_{g.name}<<<grid, block, smem, s>>>(A); return 0; }} ") if g.has_table_variant() else "if (A.tuples) return 1; "
+            src.append(f"        case {cid}: {{ {tk}static bool once = false; if (!once) {{ cudaFuncSetAttribute(g3_kernel_{g.name}, "
                        f"cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); once = true; }} "
                        f"g3_kernel_{g.name}<<<grid, block, smem, s>>>(A); return 0; }}")
             table.append((cid, pi, g.EPT, g.TPW, g.WSZ))
@@ -956,11 +977,11 @@ def write_emu_source(path, classes):
     src = ["#define SI_G3_HOST_EMU 1", HEADER.replace("../si_g3.h", "../../sympleints_b200/csrc/si_g3.h")]
     for c in classes:
         src.append(ClassGen(*c).generate())
-    src.append("struct G3EmuClass { int id, ept, tpw, wsz; void (*body)(const G3Args&, int, double*); };")
+    src.append("struct G3EmuClass { int id, ept, tpw, wsz; void (*body)(const G3Args&, int, double*); void (*tbody)(const G3Args&, int, double*); };")
     src.append("static const G3EmuClass g3_emu_classes[] = {")
     for c in classes:
         g = ClassGen(*c)
-        src.append(f"    {{{c[0] * 100 + c[1] * 10 + c[2]}, {g.EPT}, {g.TPW}, {g.WSZ}, g3_body_{g.name}}},")
+        src.append(f"    {{{c[0] * 100 + c[1] * 10 + c[2]}, {g.EPT}, {g.TPW}, {g.WSZ}, g3_body_{g.name}<false>, g3_body_{g.name}<true>}},")
     src.append("};")
     src.append(f"static const int g3_emu_nclasses = {len(classes)};")
     text = "\n".join(src) + "\n"

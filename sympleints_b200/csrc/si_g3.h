@@ -10,6 +10,12 @@
 
 #include "si_machine.h"
 
+#if defined(SI_G3_HOST_EMU)
+struct int2 {   // (built in under nvcc)
+    int x, y;
+};
+#endif
+
 struct BasisDev {
     const int* L;
     const int* nprim;
@@ -57,7 +63,8 @@ struct G3Args {
     int naux_c;
     int col_begin;
     int groups_per_pair;  // ceil(naux_c / tuples-per-warp)
-    long long ngroups;    // npairs * groups_per_pair
+    long long ngroups;    // npairs * groups_per_pair, or the number of groups listed in `tuples`
+    const int2* tuples;   // optional explicit tuple table: ngroups x tuples-per-warp entries (pair, aux), -1 = padding
     int chunk;            // unused (the kernels request one group per atomic); kept for ABI stability of the struct
     OutDesc od;
     int* counter;

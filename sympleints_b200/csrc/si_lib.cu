@@ -358,8 +358,10 @@ static int ctx_scratch(si_context* c, size_t ndoubles, cudaStream_t s, double** 
     return SI_OK;
 }
 
+static long long g_basis_uid = 0;
 struct si_basis {
     si_context* ctx = nullptr;
+    long long uid = ++g_basis_uid;   // never reused (keys of caches that outlive a basis)
     int nshell = 0;
     std::vector<int> L, nprim, poff, foff_sph, foff_cart;
     std::vector<double> cen, exps, coef, coef_pgto, oexp;
@@ -368,10 +370,17 @@ struct si_basis {
     int *d_L = nullptr, *d_nprim = nullptr, *d_poff = nullptr, *d_foff_sph = nullptr, *d_foff_cart = nullptr;
     double *d_cen = nullptr, *d_exps = nullptr, *d_coef = nullptr, *d_coef_pgto = nullptr, *d_oexp = nullptr;
     // shell-pair classes (La >= Lb), cost-sorted, on the device
+    struct TupleTable {
+        int2* d = nullptr;
+        long long ngroups = 0;
+    };
     struct PairClass {
         int La, Lb;
         int n = 0;
         SiPairItem* d_items = nullptr;
+        std::vector<std::pair<int, int>> kab;   // (Ka, Kb) of every item, in item order (host copy)
+        // explicit tuple tables for launches with few aux shells per class (key: aux uid, sb, se, Lc, tpw)
+        std::map<std::tuple<long long, int, int, int, int>, TupleTable> tables;
     };
     // A set of shell pairs (i, j), i0 <= i < i1, j <= i, sorted into (La >= Lb) classes, with the
     // precomputed primitive-pair data (9 doubles each) for coef / coef_pgto.
@@ -731,7 +740,10 @@ int si_basis_nshell(const si_basis* b) { return b ? b->nshell : -1; }
 long long si_basis_packed_rows(const si_basis* b) { return b ? b->packed_rows : -1; }
 
 static void free_pair_set(si_basis::PairSet* ps) {
-    for (auto& pc : ps->classes) cudaFree(pc.d_items);
+    for (auto& pc : ps->classes) {
+        cudaFree(pc.d_items);
+        for (auto& kv : pc.tables) cudaFree(kv.second.d);
+    }
     ps->classes.clear();
     cudaFree(ps->d_ppair[0]);
     cudaFree(ps->d_ppair[1]);
@@ -813,6 +825,7 @@ static int build_pair_set(si_basis* b, int i0, int i1, si_basis::PairSet* ps, bo
         pc.La = kv.first.first;
         pc.Lb = kv.first.second;
         pc.n = (int)v.size();
+        for (auto& x : v) pc.kab.push_back({x.Ka, x.Kb});
         SI_CUDA(cudaMalloc((void**)&pc.d_items, v.size() * sizeof(SiPairItem)));
         SI_CUDA(cudaMemcpy(pc.d_items, v.data(), v.size() * sizeof(SiPairItem), cudaMemcpyHostToDevice));
         ps->classes.push_back(pc);
@@ -1202,6 +1215,7 @@ static void g3_fill_args(G3Args& ga, si_context* c, const BasisDev& orb, const B
     ga.col_begin = col_begin;
     ga.groups_per_pair = (naux_c + tpw - 1) / tpw;
     ga.ngroups = (long long)npairs * ga.groups_per_pair;
+    ga.tuples = nullptr;
     ga.chunk = g3_chunk();
     ga.od = od;
     ga.counter = counter;
@@ -1233,6 +1247,39 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
 int si_int3c2e(si_context* c, const si_basis* corb, const si_basis* caux, int sb, int se, int normalize, int layout,
                double* out_dev, size_t out_len, void* stream) {
     return int3c2e_impl(c, corb, caux, sb, se, normalize, layout, nullptr, out_dev, out_len, stream);
+}
+
+// Explicit tuple table of one class launch: runs of pairs with equal contraction lengths, their (pair, aux)
+// tuples pair-major, tpw per group, the last group of a run padded with -1.  Built once per (aux range, class).
+static int get_tuple_table(const si_basis::PairClass* cpc, long long aux_uid, int sb, int se, int Lc, int naux_c,
+                           int tpw, const si_basis::TupleTable** out) {
+    si_basis::PairClass* pc = const_cast<si_basis::PairClass*>(cpc);
+    auto key = std::make_tuple(aux_uid, sb, se, Lc, tpw);
+    auto itb = pc->tables.find(key);
+    if (itb == pc->tables.end()) {
+        std::vector<int2> tab;
+        tab.reserve((size_t)pc->n * naux_c + 64);
+        int p0 = 0;
+        while (p0 < pc->n) {
+            int p1 = p0;
+            while (p1 < pc->n && pc->kab[p1] == pc->kab[p0]) ++p1;
+            for (int ip = p0; ip < p1; ++ip)
+                for (int ic = 0; ic < naux_c; ++ic) tab.push_back(make_int2(ip, ic));
+            while (tab.size() % tpw) tab.push_back(make_int2(-1, -1));
+            p0 = p1;
+        }
+        si_basis::TupleTable tt;
+        tt.ngroups = (long long)(tab.size() / tpw);
+        SI_CUDA(cudaMalloc((void**)&tt.d, tab.size() * sizeof(int2)));
+        SI_CUDA(cudaMemcpy(tt.d, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        if (pc->tables.size() >= 64) {   // bound the cache
+            cudaFree(pc->tables.begin()->second.d);
+            pc->tables.erase(pc->tables.begin());
+        }
+        itb = pc->tables.emplace(key, tt).first;
+    }
+    *out = &itb->second;
+    return SI_OK;
 }
 
 static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* caux, int sb, int se, int normalize,
@@ -1358,6 +1405,25 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
             G3Args ga;
             g3_fill_args(ga, c, od_orb, od_aux, aux->d_oexp, job.pc->d_items, pset->d_ppair[normalize == SI_NORM_PGTO ? 1 : 0], job.pc->n, d_list + sp.first, d_aitems + sp.first, sp.second, col_begin,
                          od, counter, g3[3]);
+            {
+                // per-pair packing leaves lanes idle when the range holds few aux shells of this class: switch to an
+                // explicit tuple table (cached) when more than ~10 % of the tuple slots would be empty
+                static int use_tables = -1;
+                if (use_tables < 0) {
+                    const char* e = getenv("SI_G3_TUPLE_TABLES");
+                    use_tables = (e && e[0] == '0') ? 0 : 1;
+                }
+                const int tpw = g3[3];
+                const double fill = (double)sp.second / ((double)ga.groups_per_pair * tpw);
+                const long long nt = (long long)job.pc->n * sp.second;
+                if (use_tables && tpw >= 4 && fill < 0.9 && pset == &orb->full && nt * 8 <= (256ll << 20)) {
+                    const si_basis::TupleTable* tt = nullptr;
+                    rc = get_tuple_table(job.pc, aux->uid, sb, se, job.Lc, sp.second, tpw, &tt);
+                    if (rc) return rc;
+                    ga.tuples = tt->d;
+                    ga.ngroups = tt->ngroups;
+                }
+            }
             int grid, block;
             size_t smem;
             if (!g3_config(c, g3, ga.ngroups, &grid, &block, &smem)) {

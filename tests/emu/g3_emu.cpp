@@ -18,7 +18,7 @@ thread_local double* si_g3_emu_smem = nullptr;
 extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, const double* da, const double* A,
                           int Kb, const double* bx, const double* db, const double* B, int naux, const int* Kc,
                           const double* cx, const double* dc, const double* C /* naux*3 */,
-                          const double* boys_table, int nrows, int ncols, const double* xlarge_pref,
+                          const double* boys_table, int nrows, int ncols, const double* xlarge_pref, int use_table,
                           double* result /* naux blocks, each (na, nb, nc) */) {
     const int id = La * 100 + Lb * 10 + Lc;
     const G3EmuClass* cls = nullptr;
@@ -92,6 +92,21 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
     args.col_begin = 0;
     args.groups_per_pair = (naux + cls->tpw - 1) / cls->tpw;
     args.ngroups = args.groups_per_pair;
+    // explicit tuple table (use_table != 0): the aux shells in reverse order, one padding slot per group
+    std::vector<int2> table;
+    if (use_table && cls->tpw > 1) {
+        int k = naux - 1;
+        while (k >= 0) {
+            for (int t = 0; t < cls->tpw; ++t) {
+                if (t == cls->tpw - 1 || k < 0)
+                    table.push_back(int2{-1, -1});
+                else
+                    table.push_back(int2{0, k--});
+            }
+        }
+        args.tuples = table.data();
+        args.ngroups = (long long)(table.size() / cls->tpw);
+    }
     args.chunk = 2;
     const int na = 2 * La + 1, nb = 2 * Lb + 1, nc = 2 * Lc + 1;
     // full layout of a 2-shell orbital basis: (nbf, nbf, naux*nc); we extract the (a, b) block afterwards
@@ -121,7 +136,7 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
             si_g3_emu_warp = &warp;
             si_g3_emu_lane = lane;
             si_g3_emu_smem = smem.data();
-            cls->body(args, lane, smem.data());
+            (args.tuples ? cls->tbody : cls->body)(args, lane, smem.data());
         });
     for (auto& t : th) t.join();
     for (int k = 0; k < naux; ++k)

@@ -117,7 +117,7 @@ def g3_lib():
     return _G3
 
 
-def g3_eval(La, Lb, Lc, shell_a, shell_b, aux_shells, table=None):
+def g3_eval(La, Lb, Lc, shell_a, shell_b, aux_shells, table=None, tuple_table=False):
     """aux_shells: list of (exps, coeffs, center) all with angular momentum Lc.  Returns
     array (naux, na, nb, nc)."""
     if table is None:
@@ -135,7 +135,7 @@ def g3_eval(La, Lb, Lc, shell_a, shell_b, aux_shells, table=None):
     res = np.zeros((naux, 2 * La + 1, 2 * Lb + 1, 2 * Lc + 1))
     rc = g3_lib().g3emu_eval(La, Lb, Lc, ax.size, _p(ax), _p(da), _p(A), bx.size, _p(bx), _p(db), _p(B), naux,
                              Kc.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _p(cx), _p(dc), _p(C), _p(table),
-                             table.shape[0], table.shape[1], _p(pref), _p(res))
+                             table.shape[0], table.shape[1], _p(pref), int(tuple_table), _p(res))
     assert rc == 0, rc
     return res
 

@@ -21,6 +21,9 @@ def test_generated_class_vs_oracle(Ls):
     # the padded primitive loop and the "repeat last valid tuple" path
     auxs = [_shell(rng, Lc, k) for k in (1, 2, 1, 3, 1, 1, 2)]
     g = emu_lib.g3_eval(La, Lb, Lc, sa, sb, auxs)
+    # the same through an explicit tuple table (reversed order, padded groups): bit-identical blocks
+    gt = emu_lib.g3_eval(La, Lb, Lc, sa, sb, auxs, tuple_table=True)
+    assert np.array_equal(g, gt)
     ld = lambda t: tuple(np.asarray(x, dtype=np.longdouble) for x in t)
     for k, sc in enumerate(auxs):
         o = ints.int3c2e_sph(La, Lb, Lc, *sa, *sb, *sc)
