@@ -11,7 +11,7 @@ hdr = rows[0]; ki = hdr.index('Kernel Name'); vi = hdr.index('Metric Value'); mi
 data = collections.defaultdict(dict)
 for r in rows[1:]:
     k = r[ki].split('(')[0]
-    if k.startswith('g3_kernel_'):
+    if k.startswith('g3_kernel_') or k.startswith('g3_tkernel_'):
         data[(r[ii], k[-3:])][r[mi]] = float(r[vi].replace(',', ''))
 per = {}
 for (id_, k), m in data.items():
