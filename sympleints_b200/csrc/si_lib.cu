@@ -1374,6 +1374,17 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
             jobs.push_back({&pc, kv.first, cost});
         }
     std::sort(jobs.begin(), jobs.end(), [](const Job& a, const Job& b) { return a.cost > b.cost; });
+    {
+        // a call that is small as a whole (the 2c2e metric, tiny systems) is launch-latency bound: use all streams
+        double total = 0.0;
+        for (auto& j : jobs) total += j.cost;
+        static double small_total = -1.0;
+        if (small_total < 0) {
+            const char* e = getenv("SI_G3_SMALL_TOTAL");
+            small_total = e ? atof(e) : 2.0e9;
+        }
+        if (2.0 * total < small_total) fan.limit = SI_NSTREAMS;
+    }
     for (auto& job : jobs) {
         DevProgram* p;
         rc = get_program(c, SI_3C2E, job.pc->La, job.pc->Lb, job.Lc, 1, normalize, &p);
