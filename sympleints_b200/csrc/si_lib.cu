@@ -613,6 +613,9 @@ static int get_program(si_context* c, int key, int La, int Lb, int Lc, int sph, 
     p->dev.terms = (const uint32_t*)p->d_terms;
     p->dev.stages = (const SiStage*)p->d_stages;
     p->dev.consts = (const double*)p->d_consts;
+    // The uploads above come from pageable memory (cudaMemcpy may return before the DMA has landed) and the
+    // kernels that read them run on non-blocking streams, possibly forked before this call: wait explicitly.
+    SI_CUDA(cudaDeviceSynchronize());
     c->progs[k] = p;
     *out = p;
     return SI_OK;
@@ -699,6 +702,7 @@ int si_basis_create(si_context* c, int nshell, const int* L, const int* nprim, c
     b->oexp.resize(np);
     for (int i = 0; i < np; ++i) b->oexp[i] = 1.0 / b->exps[i];
     SI_CUDA(upload(b->oexp, &b->d_oexp));
+    SI_CUDA(cudaDeviceSynchronize());   // pageable uploads complete before any kernel on a non-blocking stream reads them
     *out = b;
     return SI_OK;
 }
@@ -830,6 +834,8 @@ static int build_pair_set(si_basis* b, int i0, int i1, si_basis::PairSet* ps, bo
         SI_CUDA(cudaMemcpy(pc.d_items, v.data(), v.size() * sizeof(SiPairItem), cudaMemcpyHostToDevice));
         ps->classes.push_back(pc);
     }
+    // pageable uploads may still be in flight when cudaMemcpy returns; the consumers run on non-blocking streams
+    SI_CUDA(cudaDeviceSynchronize());
     return SI_OK;
 }
 
@@ -1272,6 +1278,9 @@ static int get_tuple_table(const si_basis::PairClass* cpc, long long aux_uid, in
         tt.ngroups = (long long)(tab.size() / tpw);
         SI_CUDA(cudaMalloc((void**)&tt.d, tab.size() * sizeof(int2)));
         SI_CUDA(cudaMemcpy(tt.d, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        // cudaMemcpy from pageable memory may return before the DMA has landed, and the class kernels run on
+        // non-blocking streams that were forked BEFORE this upload: wait for it explicitly (cache miss only)
+        SI_CUDA(cudaDeviceSynchronize());
         if (pc->tables.size() >= 64) {   // bound the cache
             cudaFree(pc->tables.begin()->second.d);
             pc->tables.erase(pc->tables.begin());
@@ -1341,6 +1350,7 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
         }
         SI_CUDA(cudaMalloc((void**)&r.d_items, aitems.size() * sizeof(SiAuxItem)));
         SI_CUDA(cudaMemcpy(r.d_items, aitems.data(), aitems.size() * sizeof(SiAuxItem), cudaMemcpyHostToDevice));
+        SI_CUDA(cudaDeviceSynchronize());   // (see build_pair_set)
         if (aux->aux_ranges.size() >= 64) {
             cudaFree(aux->aux_ranges.front().d_list);
             cudaFree(aux->aux_ranges.front().d_items);
