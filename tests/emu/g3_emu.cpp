@@ -15,7 +15,7 @@ thread_local SiG3EmuWarp* si_g3_emu_warp = nullptr;
 thread_local int si_g3_emu_lane = 0;
 thread_local double* si_g3_emu_smem = nullptr;
 
-extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, const double* da, const double* A,
+extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, const double* da, const double* A_,
                           int Kb, const double* bx, const double* db, const double* B, int naux, const int* Kc,
                           const double* cx, const double* dc, const double* C /* naux*3 */,
                           const double* boys_table, int nrows, int ncols, const double* xlarge_pref, int use_table,
@@ -29,7 +29,7 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
     int oL[2] = {La, Lb}, onp[2] = {Ka, Kb}, opoff[2] = {0, Ka}, ofoff[2] = {0, 2 * La + 1};
     std::vector<double> ocen(6), oex, oco;
     for (int d = 0; d < 3; ++d) {
-        ocen[d] = A[d];
+        ocen[d] = A_[d];
         ocen[3 + d] = B[d];
     }
     oex.insert(oex.end(), ax, ax + Ka);
@@ -51,14 +51,21 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
     args.aux_oexp = oexp.data();
     args.orb = BasisDev{oL, onp, opoff, ofoff, ocen.data(), oex.data(), oco.data()};
     args.aux = BasisDev{aL.data(), anp.data(), apoff.data(), afoff.data(), C, cx, dc};
-    SiPairItem item;
-    memset(&item, 0, sizeof(item));
+    // use_table == 2: a second pair (a shifted by (0.5, -0.25, 0.125), b) whose tuples are interleaved with the
+    // first pair's in the tuple table (tuples of different pairs inside one warp)
+    const int npairs = use_table == 2 ? 2 : 1;
+    const double A2[3] = {A_[0] + 0.5, A_[1] - 0.25, A_[2] + 0.125};
+    SiPairItem items[2];
+    memset(items, 0, sizeof(items));
+    SiPairItem& item = items[0];
     item.sa = 0;
     item.sb = 1;
-    std::vector<double> pp((size_t)Ka * Kb * 9);
+    std::vector<double> pp((size_t)npairs * Ka * Kb * 9);
+    for (int ipair = 0; ipair < npairs; ++ipair)
     for (int i = 0; i < Ka; ++i)
         for (int j = 0; j < Kb; ++j) {
-            double* q = &pp[(size_t)(i * Kb + j) * 9];
+            const double* A = ipair ? A2 : A_;
+            double* q = &pp[((size_t)ipair * Ka * Kb + (size_t)(i * Kb + j)) * 9];
             double p = ax[i] + bx[j], oop = 1.0 / p, mu = ax[i] * bx[j] * oop, r2 = 0.0;
             q[0] = p;
             q[1] = oop;
@@ -74,7 +81,12 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
     item.Kb = Kb;
     item.fa0 = 0;
     item.fb0 = 2 * La + 1;
-    for (int d = 0; d < 3; ++d) item.AB[d] = A[d] - B[d];
+    for (int d = 0; d < 3; ++d) item.AB[d] = A_[d] - B[d];
+    items[1] = item;
+    items[1].sa = 2;
+    items[1].ppoff = Ka * Kb;
+    items[1].fa0 = 2 * La + 1 + 2 * Lb + 1;
+    for (int d = 0; d < 3; ++d) items[1].AB[d] = A2[d] - B[d];
     std::vector<SiAuxItem> aitems(naux);
     for (int i = 0; i < naux; ++i) {
         aitems[i].shell = i;
@@ -85,8 +97,8 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
     }
     args.auxitems = aitems.data();
     args.ppair = pp.data();
-    args.pairs = &item;
-    args.npairs = 1;
+    args.pairs = items;
+    args.npairs = npairs;
     args.auxlist = alist.data();
     args.naux_c = naux;
     args.col_begin = 0;
@@ -94,14 +106,19 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
     args.ngroups = args.groups_per_pair;
     // explicit tuple table (use_table != 0): the aux shells in reverse order, one padding slot per group
     std::vector<int2> table;
-    if (use_table && cls->tpw > 1) {
-        int k = naux - 1;
+    if (use_table && (cls->tpw > 1 || use_table == 2)) {
+        int k = naux - 1, pend = 0;
         while (k >= 0) {
             for (int t = 0; t < cls->tpw; ++t) {
-                if (t == cls->tpw - 1 || k < 0)
+                if ((cls->tpw > 1 && t == cls->tpw - 1) || k < 0) {
                     table.push_back(int2{-1, -1});
-                else
+                } else if (npairs == 2) {
+                    table.push_back(int2{pend, k});
+                    if (pend == 1) --k;
+                    pend ^= 1;
+                } else {
                     table.push_back(int2{0, k--});
+                }
             }
         }
         args.tuples = table.data();
@@ -110,7 +127,7 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
     args.chunk = 2;
     const int na = 2 * La + 1, nb = 2 * Lb + 1, nc = 2 * Lc + 1;
     // full layout of a 2-shell orbital basis: (nbf, nbf, naux*nc); we extract the (a, b) block afterwards
-    const int nbf = na + nb;
+    const int nbf = na + nb + (npairs == 2 ? na : 0);
     std::vector<double> full((size_t)nbf * nbf * naux * nc, 0.0);
     args.od.out = full.data();
     args.od.ld = (long long)naux * nc;
@@ -145,5 +162,12 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
                 for (int m = 0; m < nc; ++m)
                     result[(((size_t)k * na + i) * nb + j) * nc + m] =
                         full[((size_t)i * nbf + (na + j)) * args.od.ld + (size_t)k * nc + m];
+    if (npairs == 2)
+        for (int k = 0; k < naux; ++k)
+            for (int i = 0; i < na; ++i)
+                for (int j = 0; j < nb; ++j)
+                    for (int m = 0; m < nc; ++m)
+                        result[(((size_t)(naux + k) * na + i) * nb + j) * nc + m] =
+                            full[((size_t)(na + nb + i) * nbf + (na + j)) * args.od.ld + (size_t)k * nc + m];
     return 0;
 }

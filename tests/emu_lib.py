@@ -119,7 +119,8 @@ def g3_lib():
 
 def g3_eval(La, Lb, Lc, shell_a, shell_b, aux_shells, table=None, tuple_table=False):
     """aux_shells: list of (exps, coeffs, center) all with angular momentum Lc.  Returns
-    array (naux, na, nb, nc)."""
+    array (naux, na, nb, nc).  tuple_table=True: through an explicit tuple table; tuple_table=2: additionally a
+    second pair (a shifted by (0.5, -0.25, 0.125), b) interleaved in the table; its blocks follow."""
     if table is None:
         from oracle import boys as oboys
         table = oboys.table()
@@ -132,7 +133,7 @@ def g3_eval(La, Lb, Lc, shell_a, shell_b, aux_shells, table=None, tuple_table=Fa
     dc = np.ascontiguousarray(np.concatenate([s[1] for s in aux_shells]), dtype=float)
     C = np.ascontiguousarray(np.array([s[2] for s in aux_shells], dtype=float).reshape(-1, 3))
     naux = len(aux_shells)
-    res = np.zeros((naux, 2 * La + 1, 2 * Lb + 1, 2 * Lc + 1))
+    res = np.zeros((naux * (2 if int(tuple_table) == 2 else 1), 2 * La + 1, 2 * Lb + 1, 2 * Lc + 1))
     rc = g3_lib().g3emu_eval(La, Lb, Lc, ax.size, _p(ax), _p(da), _p(A), bx.size, _p(bx), _p(db), _p(B), naux,
                              Kc.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _p(cx), _p(dc), _p(C), _p(table),
                              table.shape[0], table.shape[1], _p(pref), int(tuple_table), _p(res))

@@ -24,6 +24,13 @@ def test_generated_class_vs_oracle(Ls):
     # the same through an explicit tuple table (reversed order, padded groups): bit-identical blocks
     gt = emu_lib.g3_eval(La, Lb, Lc, sa, sb, auxs, tuple_table=True)
     assert np.array_equal(g, gt)
+    # two pairs interleaved in the table (tuples of different pairs inside one warp)
+    g2 = emu_lib.g3_eval(La, Lb, Lc, sa, sb, auxs, tuple_table=2)
+    assert np.array_equal(g2[:len(auxs)], g)
+    sa_shift = (sa[0], sa[1], np.asarray(sa[2]) + np.array([0.5, -0.25, 0.125]))
+    for k, sc in enumerate(auxs):
+        o = ints.int3c2e_sph(La, Lb, Lc, *sa_shift, *sb, *sc)
+        assert np.abs(o - g2[len(auxs) + k].ravel()).max() <= 1e-14 + 1e-11 * np.abs(o).max(), (Ls, k, "second pair")
     ld = lambda t: tuple(np.asarray(x, dtype=np.longdouble) for x in t)
     for k, sc in enumerate(auxs):
         o = ints.int3c2e_sph(La, Lb, Lc, *sa, *sb, *sc)
