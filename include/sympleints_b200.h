@@ -83,6 +83,10 @@ int si_finalize(si_context* ctx);
 int si_boys_table(const si_context* ctx, double* table, int* nrows, int* ncols);
 /* Evaluate F_n(x) for n_x arguments ON THE DEVICE (host in / host out) -- parity check of the Boys kernel. */
 int si_boys_eval(si_context* ctx, int n, const double* x, size_t n_x, double* out);
+/* The same for the evaluation variants the generated kernels use on the hot path (same table, cell and six
+ * Taylor terms; only the operation order differs): mode 0 = reference summation order (== si_boys_eval),
+ * 1 = Horner/FMA form + binary-power asymptote (3c2e / 2c2e kernels), 2 = shared-rsqrt asymptote (coul kernels). */
+int si_boys_eval_mode(si_context* ctx, int mode, int n, const double* x, size_t n_x, double* out);
 
 /*
  * Shell set (struct of arrays, host pointers; copied to the device).  coefs are the
@@ -130,6 +134,11 @@ int si_coul_h(si_context* ctx, const si_basis* basis, int sph, int normalize, in
 int si_int2c2e_h(si_context* ctx, const si_basis* aux, int sph, int normalize, double* out_host);
 int si_int3c2e_h(si_context* ctx, const si_basis* orb, const si_basis* aux, int aux_shell_begin,
                  int aux_shell_end, int normalize, int layout, double* out_host, size_t out_len);
+
+/* Timing of the last si_int3c2e_h call on this context, seconds: out[0] total, [1] host shell-batcher (0 when the
+ * row-chunk pair sets were cached), [2] staging allocation (0 when large enough), [3] host time to enqueue the chunks,
+ * [4] device time of the compute chunks, [5] wait for D2H copies after the last kernel, [6] chunks, [7] bytes per chunk. */
+int si_host_breakdown(const si_context* ctx, double* out8);
 
 /*
  * One shell block with the reference's generated-function signature

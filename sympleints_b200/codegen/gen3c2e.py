@@ -746,31 +746,6 @@ class ClassGen:
         rec([0, 0, 0], 0, 0)
         self.close()
 
-    # ---- C2S on c: Y[m][a'] = sum_c M[m][c] X[c][a'] -------------------------------------
-    def _emit_c2s_c(self):
-        E = self.emit
-        EPT = self.EPT
-        Lc = self.Lc
-        M = cart2sph(Lc)
-        f = lmn_factors(Lc)
-        n_ap = self.n_ap
-        for s in range(self.nslots(n_ap)):
-            partial = (s + 1) * EPT > n_ap
-            self.open(f"if (q + EPT * {s} < {n_ap})" if partial else "")
-            E(f"const int f_ = q + EPT * {s};")
-            for c in range(self.ncc):
-                E(f"const double x{c} = W[{self.X_OFF + c * n_ap} + f_];")
-            for m in range(self.nm):
-                terms = [(M[m][c] * f[c], c) for c in range(self.ncc) if M[m][c] != 0.0]
-                expr = None
-                for (coef, c) in terms:
-                    expr = f"{lit(coef)} * x{c}" if expr is None else f"fma({lit(coef)}, x{c}, {expr})"
-                E(f"const double y{m} = {expr};")
-            # stores after all loads (Y may not alias X: different regions)
-            for m in range(self.nm):
-                E(f"W[{self.Y_OFF + m * self.YS} + f_] = y{m};")
-            self.close()
-
     # ---- HRR tile per (target a, m) + C2S(b): Z[m][a][jb] ---------------------------------
     def _emit_hrr_c2sb(self):
         E = self.emit
@@ -932,15 +907,22 @@ def write_sources(outdir, lmax=4, lauxmax=5, nparts=15):
         for c in cl:
             g = gens[c]
             cid = c[0] * 100 + c[1] * 10 + c[2]
-            tk = (f"if (A.tuples) {{ static bool tonce = false; if (!tonce) {{ cudaFuncSetAttribute(g3_tkernel_{g.name}, "
-                  f"cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); tonce = true; }} "
-                  f"g3_tkernel_{g.name}<<<grid, block, smem, s>>>(A); return 0; }} ") if g.has_table_variant() else "if (A.tuples) return 1; "
-            src.append(f"        case {cid}: {{ {tk}static bool once = false; if (!once) {{ cudaFuncSetAttribute(g3_kernel_{g.name}, "
-                       f"cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); once = true; }} "
-                       f"g3_kernel_{g.name}<<<grid, block, smem, s>>>(A); return 0; }}")
+            tk = (f"if (A.tuples) {{ g3_tkernel_{g.name}<<<grid, block, smem, s>>>(A); return 0; }} "
+                  if g.has_table_variant() else "if (A.tuples) return 1; ")
+            src.append(f"        case {cid}: {{ {tk}g3_kernel_{g.name}<<<grid, block, smem, s>>>(A); return 0; }}")
             table.append((cid, pi, g.EPT, g.TPW, g.WSZ))
         src.append("        default: return 1;")
         src.append("    }")
+        src.append("}")
+        # the dynamic shared-memory limit is a per-device function attribute: set for every kernel of the part
+        # once per context (si_init), not behind a process-wide flag
+        src.append(f"int g3_attr_part_{pi}(int max_smem) {{")
+        for c in cl:
+            g = gens[c]
+            names = [f"g3_kernel_{g.name}"] + ([f"g3_tkernel_{g.name}"] if g.has_table_variant() else [])
+            for kn in names:
+                src.append(f"    if (cudaFuncSetAttribute({kn}, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) return 1;")
+        src.append("    return 0;")
         src.append("}")
         src.append("#endif")
         fn = os.path.join(outdir, f"g3_part_{pi:02d}.cu")
@@ -957,6 +939,15 @@ def write_sources(outdir, lmax=4, lauxmax=5, nparts=15):
     for pi, cl in enumerate(parts):
         if cl:
             lines.append(f"int g3_launch_part_{pi}(int id, const G3Args& A, int grid, int block, size_t smem, int max_smem, cudaStream_t s);")
+    for pi, cl in enumerate(parts):
+        if cl:
+            lines.append(f"int g3_attr_part_{pi}(int max_smem);")
+    lines.append("static int g3_set_attributes(int max_smem) {")
+    for pi, cl in enumerate(parts):
+        if cl:
+            lines.append(f"    if (g3_attr_part_{pi}(max_smem)) return 1;")
+    lines.append("    return 0;")
+    lines.append("}")
     lines.append("static int g3_launch(int part, int id, const G3Args& A, int grid, int block, size_t smem, int max_smem, cudaStream_t s) {")
     lines.append("    switch (part) {")
     for pi, cl in enumerate(parts):

@@ -434,13 +434,19 @@ def write_sources(outdir, lmax=4, nparts=4):
         for c in cl:
             g = gens[c]
             cid = c[0] * 10 + c[1]
-            src.append(f"        case {cid}: {{ static int occ = 0; if (!occ) {{ cudaFuncSetAttribute(gc_kernel_{g.name}, "
-                       f"cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); "
-                       f"cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gc_kernel_{g.name}, block, smem); if (occ < 1) occ = 1; }} "
+            src.append(f"        case {cid}: {{ int occ = 0; "
+                       f"if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gc_kernel_{g.name}, block, smem) != cudaSuccess || occ < 1) occ = 1; "
                        f"gc_kernel_{g.name}<<<si_g3_grid(grid, occ), block, smem, s>>>(A); return 0; }}")
             table.append((cid, pi, g.EPT, g.TPW, g.WSZ))
         src.append("        default: return 1;")
         src.append("    }")
+        src.append("}")
+        # the dynamic shared-memory limit is a per-device function attribute: set for every kernel of the part
+        # once per context (si_init), not behind a process-wide flag
+        src.append(f"int gc_attr_part_{pi}(int max_smem) {{")
+        for c in cl:
+            src.append(f"    if (cudaFuncSetAttribute(gc_kernel_{gens[c].name}, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) return 1;")
+        src.append("    return 0;")
         src.append("}")
         src.append("#endif")
         fn = _os.path.join(outdir, f"gc_part_{pi:02d}.cu")
@@ -456,6 +462,15 @@ def write_sources(outdir, lmax=4, nparts=4):
     for pi, cl in enumerate(parts):
         if cl:
             lines.append(f"int gc_launch_part_{pi}(int id, const GCArgs& A, int grid, int block, size_t smem, int max_smem, cudaStream_t s);")
+    for pi, cl in enumerate(parts):
+        if cl:
+            lines.append(f"int gc_attr_part_{pi}(int max_smem);")
+    lines.append("static int gc_set_attributes(int max_smem) {")
+    for pi, cl in enumerate(parts):
+        if cl:
+            lines.append(f"    if (gc_attr_part_{pi}(max_smem)) return 1;")
+    lines.append("    return 0;")
+    lines.append("}")
     lines.append("static int gc_launch(int part, int id, const GCArgs& A, int grid, int block, size_t smem, int max_smem, cudaStream_t s) {")
     lines.append("    switch (part) {")
     for pi, cl in enumerate(parts):

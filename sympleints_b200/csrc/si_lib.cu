@@ -12,11 +12,15 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <functional>
 #include <map>
+#include <mutex>
+#include <set>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -288,9 +292,23 @@ __global__ void k_mirror_lower(double* m, long long n) {
     if (j < n && j > i) m[i * n + j] = m[j * n + i];
 }
 
-__global__ void k_boys_eval(SiBoys Bt, int n, const double* x, size_t nx, double* out) {
+// mode 0: si_boys (the reference's summation order); 1: si_boys_fast, the variant every generated 3c2e kernel
+// calls (Horner/FMA Taylor sum on the transposed table, binary-power asymptote); 2: the variant of the generated
+// nuclear-attraction kernels (one shared rsqrt per charge, prefactor kept in a register)
+__global__ void k_boys_eval(SiBoys Bt, int mode, int n, const double* x, size_t nx, double* out) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < nx) out[i] = si_boys(Bt, n, x[i]);
+    if (i >= nx) return;
+    const double T = x[i];
+    double v;
+    if (mode == 0) {
+        v = si_boys(Bt, n, T);
+    } else if (mode == 1) {
+        v = si_boys_fast(Bt, n, T);
+    } else {
+        const double xp = Bt.xlarge_pref[n];
+        v = (T < 30.0) ? si_boys_taylor(Bt, n, T) : xp * si_boys_xpow_rs(n, si_rsqrt(T));
+    }
+    out[i] = v;
 }
 
 // ---------------------------------------------------------------------------
@@ -318,6 +336,40 @@ struct DevProgram {
 
 static const int SI_NSTREAMS = 8;
 static const int SI_NCOUNTERS = 1024;
+#define SI_GC_MAX_SPLIT 8
+
+// Tuning / debugging switches from the environment, read ONCE (C++11 thread-safe static initialisation) --
+// no lazily initialised function-level statics in the entry points.
+struct SiEnv {
+    int nstreams = SI_NSTREAMS;
+    int gc_warps_per_sm = 8, gc_max_split = SI_GC_MAX_SPLIT;
+    bool gc_profile = false, g3_profile = false, force_lut = false, force_fan = false, tuple_tables = true;
+    int g3_warps_per_block = 4, g3_grid_per_sm = 4;
+    double g3_small_total = 2.0e9, g3_big_flops = 2.5e8;
+    bool pdl = true;
+    SiEnv() {
+        auto geti = [](const char* n, int dflt) { const char* e = getenv(n); return e ? atoi(e) : dflt; };
+        auto getd = [](const char* n, double dflt) { const char* e = getenv(n); return e ? atof(e) : dflt; };
+        auto getb = [](const char* n, bool dflt) { const char* e = getenv(n); return e ? (e[0] == '1') : dflt; };
+        nstreams = std::max(1, std::min(SI_NSTREAMS, geti("SI_NSTREAMS", SI_NSTREAMS)));
+        gc_warps_per_sm = std::max(1, geti("SI_GC_WARPS_PER_SM", 8));
+        gc_max_split = std::max(1, std::min(SI_GC_MAX_SPLIT, geti("SI_GC_MAX_SPLIT", SI_GC_MAX_SPLIT)));
+        gc_profile = getb("SI_GC_PROFILE", false);
+        g3_profile = getb("SI_G3_PROFILE", false);
+        force_lut = getb("SI_FORCE_LUT", false);
+        force_fan = getb("SI_FORCE_FAN", false);
+        tuple_tables = getb("SI_G3_TUPLE_TABLES", true);
+        g3_warps_per_block = std::max(1, std::min(4, geti("SI_G3_WARPS_PER_BLOCK", 4)));
+        g3_grid_per_sm = std::max(1, geti("SI_G3_GRID_PER_SM", 4));
+        g3_small_total = getd("SI_G3_SMALL_TOTAL", 2.0e9);
+        g3_big_flops = getd("SI_G3_BIG_FLOPS", 2.5e8);
+        pdl = getb("SI_G3_PDL", true);
+    }
+};
+static const SiEnv& si_env() {
+    static const SiEnv e;
+    return e;
+}
 
 struct si_context {
     int device = 0;
@@ -336,13 +388,31 @@ struct si_context {
     cudaStream_t streams[SI_NSTREAMS];
     cudaEvent_t ev_fork;
     cudaEvent_t ev_join[SI_NSTREAMS];
+    // Calls on one context are serialised: on the host by `mu` (entry points may be called from several
+    // threads), on the device by `ev_last` (recorded when a call's work has joined the caller's stream; the
+    // next call's stream waits for it before the shared work counters are reset) -- callers may therefore
+    // pass different streams to consecutive calls.  Independent work belongs on separate contexts.
+    std::recursive_mutex mu;
+    cudaEvent_t ev_last;
+    bool ev_last_valid = false;
     int* d_counters = nullptr;
     int next_counter = 0;
     // grow-only device scratch of the coul path (charges + charge-split partial matrices): no per-call
     // allocation, whose cost through the stream-ordered pool varies by orders of magnitude
     double* d_scratch = nullptr;
     size_t scratch_doubles = 0;
+    // host-buffer 3c2e path: grow-only staging buffers, streams and events owned by the context
+    double* stage[2] = {nullptr, nullptr};
+    size_t stage_elems = 0;
+    cudaStream_t s_comp = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_done[2], ev_free[2];
+    std::vector<cudaEvent_t> ev_time;   // timing events (two per chunk), grow-only
+    double breakdown[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // of the last si_int3c2e_h call, see si_host_breakdown()
+    // shell sets by content: a set created again with identical content re-attaches to the cached object
+    // (device arrays are uploaded again, the shell-batcher's pair sets / tuple tables / aux lists are kept)
+    std::vector<struct si_basis*> basis_cache;   // least recently used first
 };
+static const size_t SI_BASIS_CACHE = 8;
 
 static int ctx_scratch(si_context* c, size_t ndoubles, cudaStream_t s, double** out) {
     if (ndoubles > c->scratch_doubles) {
@@ -358,10 +428,18 @@ static int ctx_scratch(si_context* c, size_t ndoubles, cudaStream_t s, double** 
     return SI_OK;
 }
 
-static long long g_basis_uid = 0;
+static std::atomic<long long> g_basis_uid{0};
+// live shell-set objects: a handle that outlived its context (released by si_finalize) is recognised, not dereferenced
+static std::mutex g_live_mu;
+static std::set<const void*> g_live_bases;
+static bool basis_is_live(const void* b) {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    return g_live_bases.count(b) != 0;
+}
 struct si_basis {
     si_context* ctx = nullptr;
-    long long uid = ++g_basis_uid;   // never reused (keys of caches that outlive a basis)
+    int users = 1;            // live handles returned by si_basis_create for this content
+    long long uid = g_basis_uid.fetch_add(1) + 1;   // never reused (keys of caches that outlive a basis)
     int nshell = 0;
     std::vector<int> L, nprim, poff, foff_sph, foff_cart;
     std::vector<double> cen, exps, coef, coef_pgto, oexp;
@@ -515,10 +593,22 @@ int si_init(int device, int lmax, int lauxmax, const double* boys_table, int nro
         SI_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
     SI_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    SI_CUDA(cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming));
+    SI_CUDA(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+    SI_CUDA(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        SI_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+        SI_CUDA(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+    }
     SI_CUDA(cudaMalloc(&c->d_counters, SI_NCOUNTERS * sizeof(int)));
     SI_CUDA(cudaFuncSetAttribute(k_two_index, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     SI_CUDA(cudaFuncSetAttribute(k_coul, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     SI_CUDA(cudaFuncSetAttribute(k_3c2e, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    // per-device attribute of every generated kernel (one context per device may live in the same process)
+    if (g3_set_attributes(c->max_smem) || gc_set_attributes(c->max_smem)) {
+        g_last_error = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for a generated kernel";
+        return SI_ERR_CUDA;
+    }
     *out = c;
     return SI_OK;
 }
@@ -531,15 +621,29 @@ static void free_program(DevProgram* p) {
     delete p;
 }
 
+static void basis_free(si_basis* b);
 int si_finalize(si_context* c) {
     if (!c) return SI_ERR_ARG;
     cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto* b : c->basis_cache) b->twoc_orb = nullptr;   // (internal sets are cache entries themselves)
+    for (auto* b : c->basis_cache) basis_free(b);
+    c->basis_cache.clear();
+    cudaStreamDestroy(c->s_comp);
+    cudaStreamDestroy(c->s_copy);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(c->ev_done[i]);
+        cudaEventDestroy(c->ev_free[i]);
+        cudaFree(c->stage[i]);
+    }
+    for (auto e : c->ev_time) cudaEventDestroy(e);
     for (auto& kv : c->progs) free_program(kv.second);
     for (int i = 0; i < SI_NSTREAMS; ++i) {
         cudaStreamDestroy(c->streams[i]);
         cudaEventDestroy(c->ev_join[i]);
     }
     cudaEventDestroy(c->ev_fork);
+    cudaEventDestroy(c->ev_last);
     cudaFree(c->d_boys);
     cudaFree(c->d_pref);
     cudaFree(c->d_counters);
@@ -558,14 +662,19 @@ int si_boys_table(const si_context* c, double* table, int* nrows, int* ncols) {
 }
 
 int si_boys_eval(si_context* c, int n, const double* x, size_t nx, double* out) {
-    if (!c || !x || !out) return SI_ERR_ARG;
+    return si_boys_eval_mode(c, 0, n, x, nx, out);
+}
+
+int si_boys_eval_mode(si_context* c, int mode, int n, const double* x, size_t nx, double* out) {
+    if (!c || !x || !out || mode < 0 || mode > 2) return SI_ERR_ARG;
     if (n < 0 || n > c->nrows - 7) return SI_ERR_BOYS;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     SI_CUDA(cudaSetDevice(c->device));
     double *dx = nullptr, *dout = nullptr;
     SI_CUDA(cudaMalloc(&dx, nx * sizeof(double)));
     SI_CUDA(cudaMalloc(&dout, nx * sizeof(double)));
     SI_CUDA(cudaMemcpy(dx, x, nx * sizeof(double), cudaMemcpyHostToDevice));
-    k_boys_eval<<<(unsigned)((nx + 255) / 256), 256>>>(c->boys_dev, n, dx, nx, dout);
+    k_boys_eval<<<(unsigned)((nx + 255) / 256), 256>>>(c->boys_dev, mode, n, dx, nx, dout);
     c->launches++;
     SI_CUDA(cudaGetLastError());
     SI_CUDA(cudaMemcpy(out, dout, nx * sizeof(double), cudaMemcpyDeviceToHost));
@@ -623,6 +732,7 @@ static int get_program(si_context* c, int key, int La, int Lb, int Lc, int sph, 
 
 int si_class_stats(si_context* c, int key, int La, int Lb, int Lc, int sph, int normalize, long long* out) {
     if (!c || !out) return SI_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (La < Lb) std::swap(La, Lb);
     DevProgram* p;
     int rc = get_program(c, key, La, Lb, Lc, sph, normalize, &p);
@@ -650,7 +760,34 @@ static cudaError_t upload(const std::vector<T>& v, T** d) {
 int si_basis_create(si_context* c, int nshell, const int* L, const int* nprim, const double* centers,
                     const double* exps, const double* coefs, si_basis** out) {
     if (!c || !out || nshell <= 0 || !L || !nprim || !centers || !exps || !coefs) return SI_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     SI_CUDA(cudaSetDevice(c->device));
+    {
+        // content cache: identical shell data -> the cached object (its pair sets, tuple tables and aux lists are
+        // kept); the device copies are uploaded again, so the call still moves this set's bytes host -> device
+        size_t np_ = 0;
+        for (int i = 0; i < nshell; ++i) np_ += (size_t)std::max(nprim[i], 0);
+        for (size_t ci = 0; ci < c->basis_cache.size(); ++ci) {
+            si_basis* o = c->basis_cache[ci];
+            if (o->nshell != nshell || o->exps.size() != np_) continue;
+            if (memcmp(o->L.data(), L, nshell * sizeof(int)) || memcmp(o->nprim.data(), nprim, nshell * sizeof(int)) ||
+                memcmp(o->cen.data(), centers, 3 * (size_t)nshell * sizeof(double)) ||
+                memcmp(o->exps.data(), exps, np_ * sizeof(double)) || memcmp(o->coef.data(), coefs, np_ * sizeof(double)))
+                continue;
+            if (c->ev_last_valid) SI_CUDA(cudaEventSynchronize(c->ev_last));   // no kernel of an earlier call reads them now
+            SI_CUDA(cudaMemcpy(o->d_L, L, nshell * sizeof(int), cudaMemcpyHostToDevice));
+            SI_CUDA(cudaMemcpy(o->d_nprim, nprim, nshell * sizeof(int), cudaMemcpyHostToDevice));
+            SI_CUDA(cudaMemcpy(o->d_cen, centers, 3 * (size_t)nshell * sizeof(double), cudaMemcpyHostToDevice));
+            SI_CUDA(cudaMemcpy(o->d_exps, exps, np_ * sizeof(double), cudaMemcpyHostToDevice));
+            SI_CUDA(cudaMemcpy(o->d_coef, coefs, np_ * sizeof(double), cudaMemcpyHostToDevice));
+            SI_CUDA(cudaDeviceSynchronize());
+            o->users++;
+            c->basis_cache.erase(c->basis_cache.begin() + ci);
+            c->basis_cache.push_back(o);
+            *out = o;
+            return SI_OK;
+        }
+    }
     si_basis* b = new si_basis;
     b->ctx = c;
     b->nshell = nshell;
@@ -703,14 +840,41 @@ int si_basis_create(si_context* c, int nshell, const int* L, const int* nprim, c
     for (int i = 0; i < np; ++i) b->oexp[i] = 1.0 / b->exps[i];
     SI_CUDA(upload(b->oexp, &b->d_oexp));
     SI_CUDA(cudaDeviceSynchronize());   // pageable uploads complete before any kernel on a non-blocking stream reads them
+    {
+        std::lock_guard<std::mutex> lk2(g_live_mu);
+        g_live_bases.insert(b);
+    }
+    // into the content cache; unreferenced entries beyond the limit are released, oldest first
+    c->basis_cache.push_back(b);
+    for (size_t ci = 0; c->basis_cache.size() > SI_BASIS_CACHE && ci < c->basis_cache.size();) {
+        if (c->basis_cache[ci]->users <= 0) {
+            si_basis* o = c->basis_cache[ci];
+            c->basis_cache.erase(c->basis_cache.begin() + ci);
+            basis_free(o);
+        } else {
+            ++ci;
+        }
+    }
     *out = b;
     return SI_OK;
 }
 
 static void free_pair_set(si_basis::PairSet* ps);
+// A handle is released; the object stays in the context's content cache until it is evicted or the context ends.
 int si_basis_destroy(si_basis* b) {
-    if (!b) return SI_ERR_ARG;
+    if (!b || !basis_is_live(b)) return SI_ERR_ARG;   // (also: a handle whose context is gone)
+    std::lock_guard<std::recursive_mutex> lk(b->ctx->mu);
+    if (b->users > 0) b->users--;
+    return SI_OK;
+}
+
+static void basis_free(si_basis* b) {
+    {
+        std::lock_guard<std::mutex> lk2(g_live_mu);
+        g_live_bases.erase(b);
+    }
     cudaSetDevice(b->ctx->device);
+    cudaDeviceSynchronize();
     cudaFree(b->d_L);
     cudaFree(b->d_nprim);
     cudaFree(b->d_poff);
@@ -725,7 +889,7 @@ int si_basis_destroy(si_basis* b) {
         free_pair_set(b->twoc_pairs);
         delete b->twoc_pairs;
     }
-    if (b->twoc_orb) si_basis_destroy(b->twoc_orb);
+    if (b->twoc_orb) si_basis_destroy(b->twoc_orb);   // (drops the reference; the object lives in the cache)
     for (auto& r : b->aux_ranges) {
         cudaFree(r.d_list);
         cudaFree(r.d_items);
@@ -736,7 +900,6 @@ int si_basis_destroy(si_basis* b) {
         delete ps;
     }
     delete b;
-    return SI_OK;
 }
 
 int si_basis_nbf(const si_basis* b, int sph) { return b ? (sph ? b->nbf_sph : b->nbf_cart) : -1; }
@@ -866,19 +1029,23 @@ struct Fan {
     int next = 0;
     int limit = SI_NSTREAMS;   // streams used by this fan
     bool used[SI_NSTREAMS];
+    bool open = false;
+    // The destructor joins the forked streams on every exit path (error returns inside the launch loops).
+    ~Fan() {
+        if (open) end();
+    }
     int begin() {
         memset(used, 0, sizeof(used));
+        // order this call after the previous call on this context, whatever stream that one was given
+        if (c->ev_last_valid) SI_CUDA(cudaStreamWaitEvent(user, c->ev_last, 0));
         SI_CUDA(cudaMemsetAsync(c->d_counters, 0, SI_NCOUNTERS * sizeof(int), user));
         c->next_counter = 0;
         SI_CUDA(cudaEventRecord(c->ev_fork, user));
+        open = true;
         return SI_OK;
     }
     int stream(cudaStream_t* s) {
-        static int nstreams = -1;
-        if (nstreams < 0) {
-            const char* e = getenv("SI_NSTREAMS");
-            nstreams = e ? std::max(1, std::min(SI_NSTREAMS, atoi(e))) : SI_NSTREAMS;
-        }
+        const int nstreams = si_env().nstreams;
         int i = next++ % std::min(nstreams, limit);
         if (!used[i]) {
             SI_CUDA(cudaStreamWaitEvent(c->streams[i], c->ev_fork, 0));
@@ -888,14 +1055,27 @@ struct Fan {
         return SI_OK;
     }
     int end() {
+        open = false;
         for (int i = 0; i < SI_NSTREAMS; ++i)
             if (used[i]) {
+                used[i] = false;
                 SI_CUDA(cudaEventRecord(c->ev_join[i], c->streams[i]));
                 SI_CUDA(cudaStreamWaitEvent(user, c->ev_join[i], 0));
             }
+        SI_CUDA(cudaEventRecord(c->ev_last, user));
+        c->ev_last_valid = true;
         return SI_OK;
     }
 };
+
+// marks the end of a call's device work on the caller's stream (see si_context::ev_last)
+static int mark_done(si_context* c, cudaStream_t user, int rc) {
+    if (rc == SI_OK) {
+        SI_CUDA(cudaEventRecord(c->ev_last, user));
+        c->ev_last_valid = true;
+    }
+    return rc;
+}
 
 static int pick_warps(const si_context* c, const SiProg& P, int max_warps, size_t* smem_bytes) {
     const size_t per = (size_t)((P.w_size + SI_NDYN + P.nconst + 1) & ~1) * sizeof(double);
@@ -963,7 +1143,9 @@ int si_int1e(si_context* c, const si_basis* b, int key, int sph, int normalize, 
              void* stream) {
     if (!c || !b || !out_dev) return SI_ERR_ARG;
     if (!check_key_2idx(key)) return SI_ERR_KEY;
-    return run_two_index(c, b, key, sph, normalize, R, 0, nullptr, nullptr, out_dev, (cudaStream_t)stream);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    return mark_done(c, (cudaStream_t)stream,
+                     run_two_index(c, b, key, sph, normalize, R, 0, nullptr, nullptr, out_dev, (cudaStream_t)stream));
 }
 
 static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* caux, int sb, int se, int normalize,
@@ -981,8 +1163,10 @@ static const int* gc_find(int La, int Lb) {
 int si_int2c2e(si_context* c, const si_basis* b, int sph, int normalize, double* out_dev, void* stream) {
     if (!c || !b || !out_dev) return SI_ERR_ARG;
     if (b->lmax > c->lauxmax) return SI_ERR_LMAX;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (!sph || normalize == SI_NORM_NONE || g3_disabled())
-        return run_two_index(c, b, SI_2C2E, sph, normalize, nullptr, 0, nullptr, nullptr, out_dev, (cudaStream_t)stream);
+        return mark_done(c, (cudaStream_t)stream, run_two_index(c, b, SI_2C2E, sph, normalize, nullptr, 0, nullptr, nullptr,
+                                                                out_dev, (cudaStream_t)stream));
     // Spherical 2c2e through the generated 3c2e kernels: (a|b) = (a s0|b), s0 = unit s function with exponent 0
     // (then p = a, P = A, K_ab = 1 and the 3c2e base integral reduces to the 2c2e one, defs/coulomb.py:157-160
     // vs :317-323).  Pairs (shell j, s0) in shell order give the rows of the (naux, naux) matrix.
@@ -1015,10 +1199,9 @@ int si_int2c2e(si_context* c, const si_basis* b, int sph, int normalize, double*
     k_mirror_lower<<<grid, 256, 0, (cudaStream_t)stream>>>(out_dev, (long long)n);
     c->launches++;
     SI_CUDA(cudaGetLastError());
-    return SI_OK;
+    return mark_done(c, (cudaStream_t)stream, SI_OK);
 }
 
-#define SI_GC_MAX_SPLIT 8
 // out[i] += sum_{sp >= 1} part[sp - 1][i] in a fixed order (charge-split partial matrices of the coul kernels)
 __global__ void k_sum_slices(double* out, const double* part, long long n, int nslices) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1039,6 +1222,11 @@ static int run_coul_generated(si_context* c, const si_basis* cb, int normalize, 
         g_last_error = "basis angular momentum exceeds the context limit for this key";
         return SI_ERR_LMAX;
     }
+    // highest Boys order of the basis (La + Lb <= 2 lmax) against the table (IndexError in the reference)
+    if (2 * b->lmax > c->nrows - 7) {
+        g_last_error = "Boys table too small for this basis";
+        return SI_ERR_BOYS;
+    }
     const long long nbf = b->nbf_sph;
     OutDesc od;
     od.out = out_dev;
@@ -1048,13 +1236,7 @@ static int run_coul_generated(si_context* c, const si_basis* cb, int normalize, 
     od.mode = STORE_MATRIX;
     // Charge split: a class with few shell pairs would leave most SMs idle, so its charges are divided over
     // nsplit tuples per pair; split 0 writes `out`, split sp >= 1 the slice sp-1 of a zeroed scratch buffer.
-    static int target_warps = -1, max_split = SI_GC_MAX_SPLIT;
-    if (target_warps < 0) {
-        const char* e = getenv("SI_GC_WARPS_PER_SM");
-        target_warps = c->sm_count * (e ? std::max(1, atoi(e)) : 8);
-        const char* m = getenv("SI_GC_MAX_SPLIT");
-        if (m) max_split = std::max(1, std::min(SI_GC_MAX_SPLIT, atoi(m)));
-    }
+    const int target_warps = c->sm_count * si_env().gc_warps_per_sm, max_split = si_env().gc_max_split;
     std::vector<int> nsplits;
     int top_split = 1;
     for (auto& pc : b->full.classes) {
@@ -1079,11 +1261,7 @@ static int run_coul_generated(si_context* c, const si_basis* cb, int normalize, 
         d_part = base + (size_t)4 * ncharge;
         SI_CUDA(cudaMemsetAsync(d_part, 0, (size_t)(top_split - 1) * nbf * nbf * sizeof(double), user));
     }
-    static int profile = -1;   // SI_GC_PROFILE=1: classes one after the other, each timed (tuning only)
-    if (profile < 0) {
-        const char* e = getenv("SI_GC_PROFILE");
-        profile = (e && e[0] == '1') ? 1 : 0;
-    }
+    const bool profile = si_env().gc_profile;   // SI_GC_PROFILE=1: classes one after the other, each timed (tuning only)
     Fan fan{c, user};
     rc = fan.begin();
     if (rc) return rc;
@@ -1145,6 +1323,7 @@ static int run_coul_generated(si_context* c, const si_basis* cb, int normalize, 
 int si_coul(si_context* c, const si_basis* b, int sph, int normalize, int ncharge, const double* xyz, const double* q,
             double* out_dev, void* stream) {
     if (!c || !b || !out_dev || ncharge <= 0 || !xyz || !q) return SI_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     SI_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = (cudaStream_t)stream;
     const bool generated = sph && normalize != SI_NORM_NONE && !g3_disabled() && b->lmax <= 4;
@@ -1165,12 +1344,12 @@ int si_coul(si_context* c, const si_basis* b, int sph, int normalize, int ncharg
         }
         SI_CUDA(cudaMemcpyAsync(dx, c4.data(), c4.size() * sizeof(double), cudaMemcpyHostToDevice, s));
         SI_CUDA(cudaStreamSynchronize(s));   // c4 is a temporary (pageable copies are staged, but be explicit)
-        return run_coul_generated(c, b, normalize, ncharge, dx, out_dev, s);
+        return mark_done(c, s, run_coul_generated(c, b, normalize, ncharge, dx, out_dev, s));
     }
     double* dq = dx + (size_t)3 * ncharge;
     SI_CUDA(cudaMemcpyAsync(dx, xyz, (size_t)ncharge * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
     SI_CUDA(cudaMemcpyAsync(dq, q, (size_t)ncharge * sizeof(double), cudaMemcpyHostToDevice, s));
-    return run_two_index(c, b, SI_COUL, sph, normalize, nullptr, ncharge, dx, dq, out_dev, s);
+    return mark_done(c, s, run_two_index(c, b, SI_COUL, sph, normalize, nullptr, ncharge, dx, dq, out_dev, s));
 }
 
 // ---- generated class-specialised 3c2e kernels (codegen/gen3c2e.py) ----------------------------
@@ -1181,30 +1360,8 @@ static const int* g3_find(int La, int Lb, int Lc) {
         if (g3_table[i][0] == id) return g3_table[i];
     return nullptr;
 }
-static bool g3_disabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SI_FORCE_LUT");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
-}
-static int g3_chunk() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SI_G3_CHUNK");
-        v = e ? std::max(1, atoi(e)) : 1;
-    }
-    return v;
-}
-static bool g3_profile() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SI_G3_PROFILE");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
-}
+static bool g3_disabled() { return si_env().force_lut; }
+static bool g3_profile() { return si_env().g3_profile; }
 static void g3_fill_args(G3Args& ga, si_context* c, const BasisDev& orb, const BasisDev& aux, const double* aux_oexp,
                          const SiPairItem* pairs,
                          const double* ppair, int npairs, const int* auxlist, const SiAuxItem* auxitems, int naux_c, int col_begin,
@@ -1222,27 +1379,19 @@ static void g3_fill_args(G3Args& ga, si_context* c, const BasisDev& orb, const B
     ga.groups_per_pair = (naux_c + tpw - 1) / tpw;
     ga.ngroups = (long long)npairs * ga.groups_per_pair;
     ga.tuples = nullptr;
-    ga.chunk = g3_chunk();
+    ga.chunk = 1;
     ga.od = od;
     ga.counter = counter;
     ga.boys = c->boys_dev;
 }
 static bool g3_config(const si_context* c, const int* g3, long long ngroups, int* grid, int* block, size_t* smem) {
     const size_t per_warp = (size_t)g3[4] * g3[3] * sizeof(double);  // WSZ * TPW
-    static int wpb = -1;   // warps per block (the kernels are compiled for up to 4)
-    if (wpb < 0) {
-        const char* e = getenv("SI_G3_WARPS_PER_BLOCK");
-        wpb = e ? std::max(1, std::min(4, atoi(e))) : 4;
-    }
+    const int wpb = si_env().g3_warps_per_block;   // warps per block (the kernels are compiled for up to 4)
     int nw = (int)std::min<size_t>((size_t)wpb, (size_t)c->max_smem / per_warp);
     if (nw < 1) return false;
     *block = nw * 32;
     *smem = per_warp * nw;
-    static int per_sm = -1;
-    if (per_sm < 0) {
-        const char* e = getenv("SI_G3_GRID_PER_SM");
-        per_sm = e ? std::max(1, atoi(e)) : 4;   // persistent blocks: at most 4 x 4 warps are resident per SM
-    }
+    const int per_sm = si_env().g3_grid_per_sm;   // persistent blocks: at most 4 x 4 warps are resident per SM
     *grid = (int)std::max<long long>(1, std::min<long long>((ngroups + nw - 1) / nw, (long long)c->sm_count * per_sm * (4 / nw)));
     return true;
 }
@@ -1252,6 +1401,8 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
 
 int si_int3c2e(si_context* c, const si_basis* corb, const si_basis* caux, int sb, int se, int normalize, int layout,
                double* out_dev, size_t out_len, void* stream) {
+    if (!c) return SI_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     return int3c2e_impl(c, corb, caux, sb, se, normalize, layout, nullptr, out_dev, out_len, stream);
 }
 
@@ -1388,12 +1539,7 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
         // a call that is small as a whole (the 2c2e metric, tiny systems) is launch-latency bound: use all streams
         double total = 0.0;
         for (auto& j : jobs) total += j.cost;
-        static double small_total = -1.0;
-        if (small_total < 0) {
-            const char* e = getenv("SI_G3_SMALL_TOTAL");
-            small_total = e ? atof(e) : 2.0e9;
-        }
-        if (2.0 * total < small_total) fan.limit = SI_NSTREAMS;
+        if (2.0 * total < si_env().g3_small_total) fan.limit = SI_NSTREAMS;
     }
     for (auto& job : jobs) {
         DevProgram* p;
@@ -1403,20 +1549,11 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
         cudaStream_t s;
         // launches that fill the GPU on their own run back to back on one stream (concurrent residency
         // of kernels with different shared-memory carve-outs costs more than their tails); small ones fan out
-        static int force_fan = -1;
-        if (force_fan < 0) {
-            const char* e = getenv("SI_FORCE_FAN");
-            force_fan = (e && e[0] == '1') ? 1 : 0;
-        }
+        const bool force_fan = si_env().force_fan;
         // "big" = long enough that its tail (one shell-tuple latency, 20-100 us) does not matter; shorter
         // launches (small systems, one rank's shard of many) alternate between two streams so that the
         // next kernel's blocks fill the tail of the previous one
-        static double big_flops = -1.0;
-        if (big_flops < 0) {
-            const char* e = getenv("SI_G3_BIG_FLOPS");
-            big_flops = e ? atof(e) : 2.5e8;
-        }
-        const bool big = !force_fan && 2.0 * job.cost >= big_flops;
+        const bool big = !force_fan && 2.0 * job.cost >= si_env().g3_big_flops;
         if (big) fan.next = 0;
         rc = fan.stream(&s);
         if (rc) return rc;
@@ -1429,11 +1566,7 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
             {
                 // per-pair packing leaves lanes idle when the range holds few aux shells of this class: switch to an
                 // explicit tuple table (cached) when more than ~10 % of the tuple slots would be empty
-                static int use_tables = -1;
-                if (use_tables < 0) {
-                    const char* e = getenv("SI_G3_TUPLE_TABLES");
-                    use_tables = (e && e[0] == '0') ? 0 : 1;
-                }
+                const bool use_tables = si_env().tuple_tables;
                 const int tpw = g3[3];
                 const double fill = (double)sp.second / ((double)ga.groups_per_pair * tpw);
                 const long long nt = (long long)job.pc->n * sp.second;
@@ -1507,6 +1640,7 @@ static int run_host(si_context* c, size_t n, double* out_host, const std::functi
 int si_int1e_h(si_context* c, const si_basis* b, int key, int sph, int normalize, const double* R, double* out) {
     if (!c || !b || !out) return SI_ERR_ARG;
     if (!check_key_2idx(key)) return SI_ERR_KEY;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     size_t nbf = sph ? b->nbf_sph : b->nbf_cart;
     return run_host(c, nbf * nbf * si_ncomp(key), out,
                     [&](double* d) { return si_int1e(c, b, key, sph, normalize, R, d, nullptr); });
@@ -1514,11 +1648,13 @@ int si_int1e_h(si_context* c, const si_basis* b, int key, int sph, int normalize
 int si_coul_h(si_context* c, const si_basis* b, int sph, int normalize, int ncharge, const double* xyz,
               const double* q, double* out) {
     if (!c || !b || !out) return SI_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     size_t nbf = sph ? b->nbf_sph : b->nbf_cart;
     return run_host(c, nbf * nbf, out, [&](double* d) { return si_coul(c, b, sph, normalize, ncharge, xyz, q, d, nullptr); });
 }
 int si_int2c2e_h(si_context* c, const si_basis* b, int sph, int normalize, double* out) {
     if (!c || !b || !out) return SI_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     size_t nbf = sph ? b->nbf_sph : b->nbf_cart;
     return run_host(c, nbf * nbf, out, [&](double* d) { return si_int2c2e(c, b, sph, normalize, d, nullptr); });
 }
@@ -1526,13 +1662,21 @@ int si_int2c2e_h(si_context* c, const si_basis* b, int sph, int normalize, doubl
 // k+1 computes, chunk k is copied to the caller's host buffer on a copy stream (pin the host buffer for
 // full overlap).  PACKED layout: chunks are ranges of the first shell index, i.e. contiguous row blocks
 // of the host tensor -> one contiguous cudaMemcpyAsync each.  FULL layout: chunks are aux-shell ranges
-// (column blocks, cudaMemcpy2DAsync).
+// (column blocks, cudaMemcpy2DAsync).  Staging buffers, streams and events belong to the context (grow-only);
+// the row chunking and its pair sets are cached on the (content-cached) orbital shell set.
+static double wall_now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int si_int3c2e_h(si_context* c, const si_basis* corb, const si_basis* aux, int sb, int se, int normalize, int layout,
                  double* out, size_t out_len) {
     if (!c || !corb || !aux || !out) return SI_ERR_ARG;
     if (sb < 0 || se > aux->nshell || sb >= se) return SI_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     si_basis* orb = const_cast<si_basis*>(corb);
     SI_CUDA(cudaSetDevice(c->device));
+    const double t_begin = wall_now();
+    double t_batcher = 0.0, t_alloc = 0.0;
     int rc = build_pair_classes(orb);
     if (rc) return rc;
     const long long rows = (layout == SI_LAYOUT_FULL) ? (long long)orb->nbf_sph * orb->nbf_sph : orb->packed_rows;
@@ -1543,21 +1687,41 @@ int si_int3c2e_h(si_context* c, const si_basis* corb, const si_basis* aux, int s
         g_last_error = "output buffer too small";
         return SI_ERR_ARG;
     }
-    long long stage_bytes = 1ll << 31;   // 2 GiB per staging buffer (SI_STAGE_BYTES overrides; used by the tests)
+    // staging size: at least ~12 chunks per call (compute/copy overlap needs several), 64 MiB ... 2 GiB each
+    // (SI_STAGE_BYTES overrides; used by the tests)
+    long long stage_bytes = std::min<long long>(1ll << 31, std::max<long long>(64ll << 20, rows * ncol * 8 / 12));
     if (const char* e = getenv("SI_STAGE_BYTES")) stage_bytes = std::max(1024ll, atoll(e));
-    double* stage[2] = {nullptr, nullptr};
-    cudaStream_t s_comp, s_copy;
-    cudaEvent_t ev_done[2], ev_free[2];
-    SI_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
-    SI_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-        SI_CUDA(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
-        SI_CUDA(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
-    }
-    size_t stage_elems = 0;
+    cudaStream_t s_comp = c->s_comp, s_copy = c->s_copy;
+    // order this call after earlier work of the context (the staging buffers and events are shared)
+    if (c->ev_last_valid) SI_CUDA(cudaStreamWaitEvent(s_comp, c->ev_last, 0));
+    auto ensure_stage = [&](size_t elems) -> int {
+        if (elems <= c->stage_elems) return SI_OK;
+        const double t0 = wall_now();
+        SI_CUDA(cudaDeviceSynchronize());
+        for (int i = 0; i < 2; ++i) {
+            if (c->stage[i]) SI_CUDA(cudaFree(c->stage[i]));
+            c->stage[i] = nullptr;
+        }
+        c->stage_elems = 0;
+        for (int i = 0; i < 2; ++i) SI_CUDA(cudaMalloc((void**)&c->stage[i], elems * sizeof(double)));
+        c->stage_elems = elems;
+        t_alloc += wall_now() - t0;
+        return SI_OK;
+    };
+    auto timing_events = [&](size_t n) -> int {
+        while (c->ev_time.size() < n) {
+            cudaEvent_t e;
+            SI_CUDA(cudaEventCreate(&e));
+            c->ev_time.push_back(e);
+        }
+        return SI_OK;
+    };
+    size_t nchunks = 0;
+    double t_enqueue0 = 0.0;
     if (layout == SI_LAYOUT_PACKED) {
         // (re)build the cached row chunking: consecutive first-shell ranges of <= stage_bytes each
         if (orb->row_chunks.empty() || orb->row_chunk_ncol != (int)ncol || orb->row_chunk_bytes != stage_bytes) {
+            const double t0 = wall_now();
             for (auto* ps : orb->row_chunks) {
                 free_pair_set(ps);
                 delete ps;
@@ -1572,8 +1736,8 @@ int si_int3c2e_h(si_context* c, const si_basis* corb, const si_basis* aux, int s
                 if (acc > 0 && acc + r > max_rows) {
                     auto* ps = new si_basis::PairSet;
                     rc = build_pair_set(orb, i0, i, ps);
-                    if (rc) return rc;
                     orb->row_chunks.push_back(ps);
+                    if (rc) return rc;
                     i0 = i;
                     acc = 0;
                 }
@@ -1581,25 +1745,34 @@ int si_int3c2e_h(si_context* c, const si_basis* corb, const si_basis* aux, int s
             }
             auto* ps = new si_basis::PairSet;
             rc = build_pair_set(orb, i0, orb->nshell, ps);
-            if (rc) return rc;
             orb->row_chunks.push_back(ps);
+            if (rc) return rc;
             orb->row_chunk_ncol = (int)ncol;
             orb->row_chunk_bytes = stage_bytes;
+            t_batcher += wall_now() - t0;
         }
-        for (auto* ps : orb->row_chunks) stage_elems = std::max(stage_elems, (size_t)(ps->rows * ncol));
-        for (int i = 0; i < 2; ++i) SI_CUDA(cudaMalloc((void**)&stage[i], stage_elems * sizeof(double)));
+        size_t need = 0;
+        for (auto* ps : orb->row_chunks) need = std::max(need, (size_t)(ps->rows * ncol));
+        rc = ensure_stage(need);
+        if (rc) return rc;
+        nchunks = orb->row_chunks.size();
+        rc = timing_events(2 * nchunks);
+        if (rc) return rc;
+        t_enqueue0 = wall_now();
         long long row0 = 0;
-        for (size_t k = 0; k < orb->row_chunks.size() && rc == SI_OK; ++k) {
+        for (size_t k = 0; k < nchunks && rc == SI_OK; ++k) {
             const int b = (int)(k & 1);
             auto* ps = orb->row_chunks[k];
-            if (k >= 2) SI_CUDA(cudaStreamWaitEvent(s_comp, ev_free[b], 0));
-            rc = int3c2e_impl(c, orb, aux, sb, se, normalize, layout, ps, stage[b], (size_t)(ps->rows * ncol), (void*)s_comp);
+            if (k >= 2) SI_CUDA(cudaStreamWaitEvent(s_comp, c->ev_free[b], 0));
+            SI_CUDA(cudaEventRecord(c->ev_time[2 * k], s_comp));
+            rc = int3c2e_impl(c, orb, aux, sb, se, normalize, layout, ps, c->stage[b], (size_t)(ps->rows * ncol), (void*)s_comp);
             if (rc != SI_OK) break;
-            SI_CUDA(cudaEventRecord(ev_done[b], s_comp));
-            SI_CUDA(cudaStreamWaitEvent(s_copy, ev_done[b], 0));
-            SI_CUDA(cudaMemcpyAsync(out + row0 * ncol, stage[b], (size_t)(ps->rows * ncol) * sizeof(double),
+            SI_CUDA(cudaEventRecord(c->ev_time[2 * k + 1], s_comp));
+            SI_CUDA(cudaEventRecord(c->ev_done[b], s_comp));
+            SI_CUDA(cudaStreamWaitEvent(s_copy, c->ev_done[b], 0));
+            SI_CUDA(cudaMemcpyAsync(out + row0 * ncol, c->stage[b], (size_t)(ps->rows * ncol) * sizeof(double),
                                     cudaMemcpyDeviceToHost, s_copy));
-            SI_CUDA(cudaEventRecord(ev_free[b], s_copy));
+            SI_CUDA(cudaEventRecord(c->ev_free[b], s_copy));
             row0 += ps->rows;
         }
     } else {
@@ -1621,36 +1794,61 @@ int si_int3c2e_h(si_context* c, const si_basis* corb, const si_basis* aux, int s
             int e = cuts[k + 1];
             maxc = std::max<long long>(maxc, ((e == aux->nshell) ? aux->nbf_sph : aux->foff_sph[e]) - aux->foff_sph[cuts[k]]);
         }
-        for (int i = 0; i < 2; ++i) SI_CUDA(cudaMalloc((void**)&stage[i], (size_t)rows * maxc * sizeof(double)));
+        rc = ensure_stage((size_t)rows * maxc);
+        if (rc) return rc;
+        nchunks = cuts.size() - 1;
+        rc = timing_events(2 * nchunks);
+        if (rc) return rc;
+        t_enqueue0 = wall_now();
         for (size_t k = 0; k + 1 < cuts.size() && rc == SI_OK; ++k) {
             const int b = (int)(k & 1);
             const int cs = cuts[k], ce = cuts[k + 1];
             const long long c0 = aux->foff_sph[cs] - col_begin;
             const long long cc = ((ce == aux->nshell) ? aux->nbf_sph : aux->foff_sph[ce]) - aux->foff_sph[cs];
-            if (k >= 2) SI_CUDA(cudaStreamWaitEvent(s_comp, ev_free[b], 0));
-            rc = si_int3c2e(c, orb, aux, cs, ce, normalize, layout, stage[b], (size_t)(rows * cc), (void*)s_comp);
+            if (k >= 2) SI_CUDA(cudaStreamWaitEvent(s_comp, c->ev_free[b], 0));
+            SI_CUDA(cudaEventRecord(c->ev_time[2 * k], s_comp));
+            rc = int3c2e_impl(c, orb, aux, cs, ce, normalize, layout, nullptr, c->stage[b], (size_t)(rows * cc), (void*)s_comp);
             if (rc != SI_OK) break;
-            SI_CUDA(cudaEventRecord(ev_done[b], s_comp));
-            SI_CUDA(cudaStreamWaitEvent(s_copy, ev_done[b], 0));
-            SI_CUDA(cudaMemcpy2DAsync(out + c0, (size_t)ncol * sizeof(double), stage[b], (size_t)cc * sizeof(double),
+            SI_CUDA(cudaEventRecord(c->ev_time[2 * k + 1], s_comp));
+            SI_CUDA(cudaEventRecord(c->ev_done[b], s_comp));
+            SI_CUDA(cudaStreamWaitEvent(s_copy, c->ev_done[b], 0));
+            SI_CUDA(cudaMemcpy2DAsync(out + c0, (size_t)ncol * sizeof(double), c->stage[b], (size_t)cc * sizeof(double),
                                       (size_t)cc * sizeof(double), (size_t)rows, cudaMemcpyDeviceToHost, s_copy));
-            SI_CUDA(cudaEventRecord(ev_free[b], s_copy));
+            SI_CUDA(cudaEventRecord(c->ev_free[b], s_copy));
         }
     }
+    const double t_enqueued = wall_now();
     cudaError_t e1 = cudaStreamSynchronize(s_comp);
+    const double t_comp_done = wall_now();
     cudaError_t e2 = cudaStreamSynchronize(s_copy);
-    for (int i = 0; i < 2; ++i) {
-        cudaFree(stage[i]);
-        cudaEventDestroy(ev_done[i]);
-        cudaEventDestroy(ev_free[i]);
-    }
-    cudaStreamDestroy(s_comp);
-    cudaStreamDestroy(s_copy);
+    const double t_end = wall_now();
+    // later calls on the context (any stream) are ordered after this one
+    if (cudaEventRecord(c->ev_last, s_copy) == cudaSuccess) c->ev_last_valid = true;
     if (rc == SI_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
         g_last_error = cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);
         rc = SI_ERR_CUDA;
     }
+    double t_kernels = 0.0;
+    if (rc == SI_OK)
+        for (size_t k = 0; k < nchunks; ++k) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c->ev_time[2 * k], c->ev_time[2 * k + 1]) == cudaSuccess) t_kernels += ms * 1e-3;
+        }
+    c->breakdown[0] = t_end - t_begin;           // total
+    c->breakdown[1] = t_batcher;                 // host shell-batcher (row-chunk pair sets; 0 when cached)
+    c->breakdown[2] = t_alloc;                   // staging (re)allocation (0 when large enough)
+    c->breakdown[3] = t_enqueued - t_enqueue0;   // host time to enqueue all chunks (launches + copies)
+    c->breakdown[4] = t_kernels;                 // device time of the compute chunks (sum of per-chunk event times)
+    c->breakdown[5] = t_end - t_comp_done;       // wait for the copies after the last kernel finished
+    c->breakdown[6] = (double)nchunks;
+    c->breakdown[7] = (double)stage_bytes;
     return rc;
+}
+
+int si_host_breakdown(const si_context* c, double* out8) {
+    if (!c || !out8) return SI_ERR_ARG;
+    memcpy(out8, c->breakdown, sizeof(c->breakdown));
+    return SI_OK;
 }
 
 // ---- FP64 peak microbenchmark (roofline denominator; not in MEASURED_PEAKS.json) ------------------
@@ -1710,6 +1908,7 @@ int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int n
                   int Kc, const double* cx, const double* dc, const double* C, const double* R, double* result) {
     if (!c || !ax || !da || !A || !bx || !db || !B || !result || Ka <= 0 || Kb <= 0) return SI_ERR_ARG;
     if (key < 0 || key > SI_3C2E) return SI_ERR_KEY;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     const bool three = (key == SI_3C2E);
     if (three && (!cx || !dc || !C || Kc <= 0)) return SI_ERR_ARG;
     if (three) sph = 1;
@@ -1826,8 +2025,9 @@ int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int n
                 g3_fill_args(ga, c, bd, ad, xb->d_oexp, d_item, d_pp, 1, d_list1, d_aitem, 1, 0, od, d_counter, g3[3]);
                 int grid, block;
                 size_t sm2;
-                if (e == cudaSuccess && g3_config(c, g3, ga.ngroups, &grid, &block, &sm2))
-                    g3_launch(g3[1], g3[0], ga, 1, 32, (size_t)g3[4] * g3[3] * sizeof(double), c->max_smem, 0);
+                if (e == cudaSuccess && g3_config(c, g3, ga.ngroups, &grid, &block, &sm2) &&
+                    g3_launch(g3[1], g3[0], ga, 1, 32, (size_t)g3[4] * g3[3] * sizeof(double), c->max_smem, 0))
+                    e = cudaErrorInvalidDeviceFunction;
                 if (e == cudaSuccess) e = cudaDeviceSynchronize();
                 cudaFree(d_list1);
                 cudaFree(d_pp);

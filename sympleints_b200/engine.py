@@ -5,6 +5,7 @@ that device.  PyTorch is used for buffer ownership and streams only; all
 arithmetic happens in the CUDA kernels of libsympleints_b200.so.
 """
 import ctypes
+import weakref
 from ctypes import c_double, c_int, c_longlong, c_void_p
 
 import numpy as np
@@ -40,6 +41,7 @@ class Basis:
         check(engine.lib.si_basis_create(engine.ctx, len(self.shells), _ip(L), _ip(nprim), _dp(centers),
                                          _dp(exps), _dp(coefs), ctypes.byref(h)))
         self.handle = h
+        engine._bases.add(self)
         self.nshell = len(self.shells)
         self.nbf_sph = engine.lib.si_basis_nbf(h, 1)
         self.nbf_cart = engine.lib.si_basis_nbf(h, 0)
@@ -52,7 +54,8 @@ class Basis:
 
     def close(self):
         if self.handle is not None:
-            self.engine.lib.si_basis_destroy(self.handle)
+            if getattr(self.engine, "ctx", None) is not None:   # the context releases its shell sets itself
+                self.engine.lib.si_basis_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -77,11 +80,14 @@ class Engine:
         else:
             check(self.lib.si_init(self.device, lmax, lauxmax, None, 0, 0, ctypes.byref(ctx)))
         self.ctx = ctx
+        self._bases = weakref.WeakSet()
         self.tdev = self.torch.device("cuda", self.device)
 
     # -- plumbing ---------------------------------------------------------
     def close(self):
         if getattr(self, "ctx", None) is not None:
+            for b in list(self._bases):
+                b.handle = None
             self.lib.si_finalize(self.ctx)
             self.ctx = None
 
@@ -107,10 +113,14 @@ class Engine:
         check(self.lib.si_boys_table(self.ctx, _dp(tab), None, None))
         return tab
 
-    def boys(self, n, xs):
+    BOYS_MODES = {"reference": 0, "fast": 1, "coul": 2}
+
+    def boys(self, n, xs, mode="reference"):
+        """F_n(xs) on the device.  ``mode``: 'reference' (summation order of testing/boys.py), 'fast' (the
+        variant the generated 3c2e/2c2e kernels call), 'coul' (the variant of the generated coul kernels)."""
         xs = np.ascontiguousarray(xs, dtype=np.float64)
         out = np.empty_like(xs)
-        check(self.lib.si_boys_eval(self.ctx, int(n), _dp(xs), xs.size, _dp(out)))
+        check(self.lib.si_boys_eval_mode(self.ctx, self.BOYS_MODES[mode], int(n), _dp(xs), xs.size, _dp(out)))
         return out
 
     def fp64_peak(self, seconds=0.5):
@@ -202,6 +212,13 @@ class Engine:
         check(self.lib.si_int3c2e_h(self.ctx, orb.handle, aux.handle, sb, se, NORMALIZE[normalize], LAYOUT[layout],
                                     _dp(out), out.size))
         return out
+
+    def host_breakdown(self):
+        """Timing of the last ``int3c2e_host`` call (si_host_breakdown)."""
+        out = np.zeros(8)
+        check(self.lib.si_host_breakdown(self.ctx, _dp(out)))
+        return {"total_s": out[0], "batcher_s": out[1], "alloc_s": out[2], "enqueue_s": out[3], "compute_s": out[4],
+                "copy_wait_s": out[5], "chunks": int(out[6]), "chunk_bytes": int(out[7])}
 
     # -- one block, generated-function signature ------------------------------
     def eval_block(self, key, Ls, ax, da, A, bx, db, B, cx=None, dc=None, C=None, R=None, result=None,

@@ -28,6 +28,7 @@ SIGNATURES = {
     "si_finalize": (c_int, [c_void_p]),
     "si_boys_table": (c_int, [c_void_p, c_double_p, c_int_p, c_int_p]),
     "si_boys_eval": (c_int, [c_void_p, c_int, c_double_p, c_size_t, c_double_p]),
+    "si_boys_eval_mode": (c_int, [c_void_p, c_int, c_int, c_double_p, c_size_t, c_double_p]),
     "si_basis_create": (c_int, [c_void_p, c_int, c_int_p, c_int_p, c_double_p, c_double_p, c_double_p, POINTER(c_void_p)]),
     "si_basis_destroy": (c_int, [c_void_p]),
     "si_basis_nbf": (c_int, [c_void_p, c_int]),
@@ -46,6 +47,7 @@ SIGNATURES = {
                               c_int, c_double_p, c_double_p, c_double_p,
                               c_int, c_double_p, c_double_p, c_double_p,
                               c_double_p, c_double_p]),
+    "si_host_breakdown": (c_int, [c_void_p, c_double_p]),
     "si_fp64_peak": (c_int, [c_void_p, c_double, c_double_p]),
     "si_launch_count": (c_longlong, [c_void_p]),
     "si_class_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_longlong)]),

@@ -1,0 +1,227 @@
+"""GPU parity AT THE BENCHMARK'S OWN SIZES (BASELINE.json configs 2-5):
+50 atoms, 300 orbital shells / 1300 functions, 1200 aux shells / 5000 functions, 1024 charges.
+
+The full tensors are produced on the GPU through the C ABI; sampled shell blocks (stratified over the
+angular-momentum classes, both shell orders) are compared with the REFERENCE's own generated numpy
+modules (oracle/_ref, float64 and extended precision; criterion of tests/golden_util.py), falling back
+to the pinned numpy port oracle/ints.py when oracle/_ref was not generated.  Reference driver being
+mirrored: sympleints/testing/intor.py:18-76, tests/test_intor/test_intor.py:37-43 (charge sum).
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import ints, refmod
+from sympleints_b200 import dist as sdist
+from sympleints_b200 import synthetic, workmodel
+
+pytestmark = pytest.mark.gpu
+
+HAVE_REF = all(refmod.available(k) for k in ("ovlp", "kin", "dpm", "qpm", "dqpm", "coul", "2c2e", "3c2e"))
+
+
+@pytest.fixture(scope="module")
+def system(engine):
+    shells, sites = synthetic.orbital_basis(natoms=50)
+    aux = synthetic.aux_basis(sites)
+    assert len(shells) == 300 and sum(2 * s.L + 1 for s in shells) == 1300
+    assert len(aux) == 1200 and sum(2 * s.L + 1 for s in aux) == 5000
+    return dict(shells=shells, sites=sites, aux=aux, ob=engine.basis(shells), ab=engine.basis(aux),
+                offo=np.concatenate([[0], np.cumsum([2 * s.L + 1 for s in shells])]),
+                offa=np.concatenate([[0], np.cumsum([2 * s.L + 1 for s in aux])]))
+
+
+def _pair_block_ref(key, a, b, R, dtype):
+    if HAVE_REF:
+        return refmod.eval_pair(key, a, b, R=R, dtype=dtype)
+    f, ncomp = ints.KEY_FUNCS[key]
+    c = lambda x: np.asarray(x, dtype=dtype)
+    return f(a.L, b.L, c(a.exps), c(a.coeffs), c(a.center), c(b.exps), c(b.coeffs), c(b.center), R=c(R),
+             sph=True, normalize="cgto").reshape(ncomp, 2 * a.L + 1, 2 * b.L + 1)
+
+
+def _sample_pairs(shells, per_combo, seed):
+    """Ordered shell pairs (i, j), `per_combo` for every ordered (L_i, K_i, L_j, K_j) combination: covers the
+    15 native (La >= Lb) classes, the 10 swapped ones and every contraction length."""
+    rng = np.random.default_rng(seed)
+    by = {}
+    for i, s in enumerate(shells):
+        by.setdefault((s.L, len(s.exps)), []).append(i)
+    out = []
+    for ka, kb in itertools.product(sorted(by), repeat=2):
+        for _ in range(per_combo):
+            out.append((int(rng.choice(by[ka])), int(rng.choice(by[kb]))))
+    return out
+
+
+@pytest.mark.parametrize("key", ["ovlp", "kin", "dpm", "qpm", "dqpm"])
+def test_one_electron_matrices_at_1300_functions(engine, system, key):
+    shells, ob, off = system["shells"], system["ob"], system["offo"]
+    R = np.array([0.0, 0.0, 0.0]) if key in ("ovlp", "kin") else np.array([1.5, -0.7, 2.2])
+    M = engine.int1e(key, ob, R=R)
+    M = M.reshape(-1, 1300, 1300)
+    bad = []
+    pairs = _sample_pairs(shells, 2, seed=3)
+    assert len(pairs) >= 72
+    for (i, j) in pairs:
+        g = M[:, off[i]:off[i + 1], off[j]:off[j + 1]].cpu().numpy()
+        r64 = _pair_block_ref(key, shells[i], shells[j], R, np.float64)
+        r80 = _pair_block_ref(key, shells[i], shells[j], R, np.longdouble)
+        ok, ratio = refmod.block_check(g, r64, r80)
+        if not ok:
+            bad.append((i, j, ratio))
+    assert not bad, bad[:5]
+    # Hermitian, mirrored exactly
+    assert float((M - M.transpose(1, 2)).abs().max()) <= 1e-15 * float(M.abs().max())
+
+
+def _coul_block_ref(a, b, xyz, q, dtype):
+    """sum_C q_C (a|1/|r - R_C||b) in ONE call of the reference's generated function: the charge axis is a
+    leading broadcast axis (R[i] has shape (nC, 1, 1), q is folded into da), numpy.sum reduces it."""
+    c = lambda x: np.asarray(x, dtype=dtype)
+    if HAVE_REF:
+        fd = refmod.funcs("coul")
+        res = np.zeros((2 * a.L + 1) * (2 * b.L + 1), dtype=dtype)
+        Rb = c(xyz).T.reshape(3, -1, 1, 1)
+        da = c(q).reshape(-1, 1, 1) * c(a.coeffs).reshape(1, -1, 1)
+        fd[(a.L, b.L)](c(a.exps).reshape(1, -1, 1), da, c(a.center), c(b.exps).reshape(1, 1, -1),
+                       c(b.coeffs).reshape(1, 1, -1), c(b.center), Rb, res)
+        return res.reshape(2 * a.L + 1, 2 * b.L + 1)
+    tot = 0
+    for rr, qq in zip(xyz, q):
+        tot = tot + qq * ints.coul(a.L, b.L, c(a.exps), c(a.coeffs), c(a.center), c(b.exps), c(b.coeffs), c(b.center),
+                                   R=c(rr), sph=True, normalize="cgto")
+    return np.asarray(tot).reshape(2 * a.L + 1, 2 * b.L + 1)
+
+
+def test_nuclear_attraction_1024_charges(engine, system):
+    """Config 3: the 8-way charge split and the 15 generated gc_kernel classes at full size."""
+    shells, sites, ob, off = system["shells"], system["sites"], system["ob"], system["offo"]
+    xyz, q = synthetic.point_charges(sites, n=1024)
+    V = engine.coul(ob, xyz, q)
+    assert float((V - V.T).abs().max()) <= 1e-15 * float(V.abs().max())
+    pairs = _sample_pairs(shells, 1, seed=5)
+    bad = []
+    for (i, j) in pairs:
+        a, b = shells[i], shells[j]
+        g = V[off[i]:off[i + 1], off[j]:off[j + 1]].cpu().numpy()
+        r64 = _coul_block_ref(a, b, xyz, q, np.float64)
+        # the charge sum cancels heavily (q of both signs): judge on the scale of the summed magnitudes
+        scale = float(np.abs(_coul_block_ref(a, b, xyz[:64], np.abs(q[:64]), np.float64)).max()) * (1024 / 64)
+        if np.abs(g - r64).max() > 1e-14 + 1e-12 * max(scale, float(np.abs(r64).max())):
+            bad.append((i, j, float(np.abs(g - r64).max()), scale))
+    assert not bad, bad[:5]
+
+
+def test_two_center_metric_at_5000_functions(engine, system):
+    aux, ab, off = system["aux"], system["ab"], system["offa"]
+    M = engine.int2c2e(ab)
+    assert float((M - M.T).abs().max()) == 0.0
+    bad = []
+    for (i, j) in _sample_pairs(aux, 3, seed=7):
+        g = M[off[i]:off[i + 1], off[j]:off[j + 1]].cpu().numpy()[None]
+        r64 = _pair_block_ref("2c2e", aux[i], aux[j], np.zeros(3), np.float64)
+        r80 = _pair_block_ref("2c2e", aux[i], aux[j], np.zeros(3), np.longdouble)
+        ok, ratio = refmod.block_check(g, r64, r80)
+        if not ok:
+            bad.append((i, j, ratio))
+    assert not bad, bad[:5]
+
+
+def _triple_ref(a, b, c, dtype):
+    if HAVE_REF:
+        return refmod.eval_triple(a, b, c, dtype)
+    cv = lambda x: np.asarray(x, dtype=dtype)
+    return ints.int3c2e_sph(a.L, b.L, c.L, cv(a.exps), cv(a.coeffs), cv(a.center), cv(b.exps), cv(b.coeffs),
+                            cv(b.center), cv(c.exps), cv(c.coeffs), cv(c.center)).reshape(2 * a.L + 1, 2 * b.L + 1, -1)
+
+
+def _packed_row_starts(shells):
+    sizes = np.array([2 * s.L + 1 for s in shells], dtype=np.int64)
+    csum = np.concatenate([[0], np.cumsum(sizes)])
+    # rows before shell i: sum_{i' < i} n_i' * (n_0 + ... + n_i')
+    before = np.concatenate([[0], np.cumsum(sizes * csum[1:])])
+    return sizes, csum, before
+
+
+def _check_slab(T, shells, aux, sb, se, triples):
+    """T: (packed_rows, ncol) slab of aux shells [sb, se).  Returns the failing triples."""
+    sizes, csum, before = _packed_row_starts(shells)
+    offa = np.concatenate([[0], np.cumsum([2 * s.L + 1 for s in aux])])
+    bad = []
+    for (i, j, k) in triples:
+        assert j <= i and sb <= k < se
+        r0 = int(before[i] + sizes[i] * csum[j])
+        n = int(sizes[i] * sizes[j])
+        c0 = int(offa[k] - offa[sb])
+        g = T[r0:r0 + n, c0:c0 + 2 * aux[k].L + 1]
+        g = (g.cpu().numpy() if hasattr(g, "cpu") else np.asarray(g)).reshape(sizes[i], sizes[j], -1)
+        r64 = _triple_ref(shells[i], shells[j], aux[k], np.float64)
+        r80 = _triple_ref(shells[i], shells[j], aux[k], np.longdouble)
+        ok, ratio = refmod.block_check(g, r64, r80)
+        if not ok:
+            bad.append((i, j, k, ratio))
+    return bad
+
+
+def _sample_triples(shells, aux, sb, se, per_class, seed):
+    """(i >= j, k) triples: `per_class` for every (L_i,K_i,L_j,K_j) x L_k combination present in the range."""
+    rng = np.random.default_rng(seed)
+    pairs = {}
+    for i, a in enumerate(shells):
+        for j in range(i + 1):
+            b = shells[j]
+            key = (a.L, len(a.exps), b.L, len(b.exps))
+            lst = pairs.setdefault(key, [])
+            if len(lst) < 64:
+                lst.append((i, j))
+    auxby = {}
+    for k in range(sb, se):
+        auxby.setdefault(aux[k].L, []).append(k)
+    out = []
+    for key in sorted(pairs):
+        for lc in sorted(auxby):
+            for _ in range(per_class):
+                i, j = pairs[key][rng.integers(len(pairs[key]))]
+                out.append((i, j, int(rng.choice(auxby[lc]))))
+    return out
+
+
+def test_three_center_tensor_every_rank_shard_of_8(engine, system):
+    """Config 5: the slab each of 8 ranks computes (cost-balanced contiguous aux-shell ranges, tuple-table
+    kernels where a class has few aux shells in the range), sampled over all classes in the range."""
+    shells, aux, ob, ab = system["shells"], system["aux"], system["ob"], system["ab"]
+    ranges = sdist.partition_aux_shells(workmodel.aux_shell_costs(shells, aux), 8)
+    assert ranges[0][0] == 0 and ranges[-1][1] == 1200
+    nchecked = 0
+    for r, (sb, se) in enumerate(ranges):
+        T = engine.int3c2e(ob, ab, shell_range=(sb, se), layout="packed")
+        triples = _sample_triples(shells, aux, sb, se, 1, seed=100 + r)[::3]
+        bad = _check_slab(T, shells, aux, sb, se, triples)
+        assert not bad, (r, bad[:5])
+        nchecked += len(triples)
+        if r == 3:
+            # host-buffer path of the same shard (row-chunked staging, D2H) is bit-identical
+            h = engine.int3c2e_host(ob, ab, shell_range=(sb, se), layout="packed")
+            idx = np.random.default_rng(0).integers(0, h.shape[0], 4000)
+            assert np.array_equal(h[idx], T[idx].cpu().numpy())
+            assert np.array_equal(h[-1], T[-1].cpu().numpy())
+        del T
+    assert nchecked >= 300
+
+
+def test_three_center_tensor_full_range_single_gpu(engine, system):
+    """The N = 1 configuration of the benchmark: all 1200 aux shells in one call (34 GB slab)."""
+    shells, aux, ob, ab = system["shells"], system["aux"], system["ob"], system["ab"]
+    T = engine.int3c2e(ob, ab, layout="packed")
+    assert tuple(T.shape) == (ob.packed_rows, 5000)
+    triples = _sample_triples(shells, aux, 0, 1200, 2, seed=9)
+    assert len(triples) >= 300
+    bad = _check_slab(T, shells, aux, 0, 1200, triples)
+    assert not bad, bad[:5]
+    # idempotence of the step the benchmark repeats: a second evaluation into the same buffer is bit-identical
+    rows = np.random.default_rng(1).integers(0, T.shape[0], 2000)
+    before = T[rows].clone()
+    engine.int3c2e(ob, ab, layout="packed", out=T)
+    assert bool((T[rows] == before).all())

@@ -28,6 +28,70 @@ def test_boys_kernel_matches_reference_values(engine):
         np.testing.assert_allclose(got, vals[n], rtol=5e-15, atol=0, err_msg=f"n={n}")
 
 
+@pytest.mark.parametrize("mode,rtol", [("fast", 5e-15), ("coul", 5e-15)])
+def test_hot_path_boys_variants_match_reference_values(engine, mode, rtol):
+    """The variants the generated kernels actually call (si_boys_fast: Horner/FMA Taylor sum on the
+    transposed table + binary-power asymptote; the coul kernels' shared-rsqrt asymptote) against the
+    reference's golden values.  Same table, same cell, same six terms: the stated bound is 5e-15 relative (23 ulp
+    of 2.2e-16; measured worst case 2.4e-15 in the asymptotic branch at x = 200, where x^(-n-1/2) is built from
+    ~10 multiplications), 200 times below the 1e-12 parity tolerance."""
+    z = np.load(gu.GOLDEN / "boys_golden.npz")
+    xs, vals = z["xs"], z["vals"]
+    worst = 0.0
+    for n in range(vals.shape[0]):
+        got = engine.boys(n, xs, mode=mode)
+        rel = np.abs(got - vals[n]) / np.abs(vals[n])
+        worst = max(worst, float(rel.max()))
+        np.testing.assert_allclose(got, vals[n], rtol=rtol, atol=0, err_msg=f"mode={mode} n={n}")
+    assert worst > 0.0  # a different operation order than mode 'reference', not an alias of it
+
+
+def _two_shell_block(engine, blk, sph, normalize):
+    """A golden (a|b) block through the BATCHED entry points: a two-shell basis, off-diagonal block of the
+    matrix -- the vectors hit the generated gc_kernel_* / the (a s0|b) 2c2e path, not the single-block entry."""
+    from sympleints_b200.shells import Shell
+
+    (ax, da, A), (bx, db, B) = blk["a"], blk["b"]
+    La, Lb = blk["Ls"]
+    basis = engine.basis([Shell(La, A, da, ax, normalized=True), Shell(Lb, B, db, bx, normalized=True)])
+    size = (lambda l: 2 * l + 1) if sph else (lambda l: (l + 1) * (l + 2) // 2)
+    na, nb = size(La), size(Lb)
+    if blk["key"] == "coul":
+        M = engine.coul(basis, blk["R"].reshape(1, 3), np.ones(1), sph=sph, normalize=normalize).cpu().numpy()
+    else:
+        M = engine.int2c2e(basis, sph=sph, normalize=normalize).cpu().numpy()
+    assert np.array_equal(M[:na, na:], M[na:, :na].T)
+    return M[:na, na:na + nb].ravel()
+
+
+@pytest.mark.parametrize("variant", gu.variants())
+def test_golden_coul_and_2c2e_blocks_through_batched_kernels(engine, variant):
+    sph, normalize, blocks = gu.load_variant(variant)
+    bad, n = [], 0
+    for blk in blocks:
+        if blk["key"] not in ("coul", "2c2e"):
+            continue
+        n += 1
+        ok, rep = gu.block_error(_two_shell_block(engine, blk, sph, normalize), blk)
+        if not ok:
+            bad.append(rep)
+    assert not bad, bad[:5]
+    if variant == "sph_cgto_l4_laux5":
+        assert n == 20 + 26   # 15 + 5 swapped coul classes, 21 + 5 swapped 2c2e classes
+
+
+def test_coul_rejects_a_boys_table_that_is_too_small():
+    """The batched coul path checks the Boys order against the caller's table (IndexError in the reference)."""
+    import sympleints_b200
+    from sympleints_b200.shells import Shell
+
+    small = sympleints_b200.get_engine(0, 4, 5, boys_table=oboys.build_table(2)[1])   # rows for n <= 2
+    sh = [Shell(2, [0.0, 0.0, 0.0], [1.0], [1.0]), Shell(1, [0.5, 0.0, 0.0], [1.0], [0.7])]
+    with pytest.raises(sympleints_b200.SympleintsB200Error, match="Boys"):
+        small.coul(small.basis(sh), np.zeros((1, 3)), np.ones(1))
+    small.close()
+
+
 def test_own_boys_table_is_accurate():
     """Without a caller-supplied table the library builds its own; it must agree with quadrature
     better than the reference's table does (the reference's depends on nmax at the 1e-9 level)."""
