@@ -109,6 +109,10 @@ long long si_basis_packed_rows(const si_basis* basis);
  */
 int si_int1e(si_context* ctx, const si_basis* basis, int key, int sph, int normalize, const double* R,
              double* out_dev, void* stream);
+/* The whole one-electron set in one call (one kernel launch for sph + cgto|pgto): out_dev = (11, nbf, nbf):
+ * component 0 ovlp, 1 kin, 2-4 dpm x,y,z, 5-10 qpm xx,xy,xz,yy,yz,zz. */
+int si_int1e_set(si_context* ctx, const si_basis* basis, int sph, int normalize, const double* R, double* out_dev,
+                 void* stream);
 /*
  * Nuclear attraction / external potential: out[mu,nu] = sum_C q[C] * (mu| 1/|r-R_C| |nu).
  * The generated coulomb3d functions return the integral for a unit positive charge

@@ -1,4 +1,4 @@
-"""Time the 1e matrices of the benchmark system."""
+"""Time the fused one-electron kernel (si_int1e_set) and the per-key calls on the benchmark basis."""
 import sys
 from pathlib import Path
 
@@ -6,24 +6,33 @@ import numpy as np
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import sympleints_b200
 from sympleints_b200 import synthetic
-from sympleints_b200.engine import Engine
 
-keys = sys.argv[1].split(",") if len(sys.argv) > 1 else ["ovlp", "kin", "dpm", "qpm"]
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-eng = Engine()
-shells, sites = synthetic.orbital_basis()
+eng = sympleints_b200.get_engine(0, 4, 5)
+shells, sites = synthetic.orbital_basis(natoms=50)
 ob = eng.basis(shells)
-for key in keys:
-    ncomp = {"ovlp": 1, "kin": 1, "dpm": 3, "qpm": 6, "dqpm": 3}[key]
-    buf = torch.empty((ncomp, ob.nbf_sph, ob.nbf_sph), dtype=torch.float64, device=eng.tdev)
-    eng.int1e(key, ob, out=buf)
+nbf = ob.nbf_sph
+buf = torch.empty((11, nbf, nbf), dtype=torch.float64, device=eng.tdev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.tdev)
+
+
+def timeit(fn, reps=20):
+    fn()
     torch.cuda.synchronize()
+    ts = []
     for _ in range(reps):
+        flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        eng.int1e(key, ob, out=buf)
+        fn()
         e1.record()
         torch.cuda.synchronize()
-        print("%s: %.3f ms" % (key, e0.elapsed_time(e1)), flush=True)
-    print(key, "checksum", float(buf.sum()), float(buf.abs().max()))
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    return float(np.median(ts)), float(np.min(ts))
+
+
+print("set (11 comps): median %.1f us, min %.1f us  -> %.0f GB/s" % (*timeit(lambda: eng.int1e_set(ob, out=buf)), 8 * 11 * nbf * nbf / timeit(lambda: eng.int1e_set(ob, out=buf))[0] / 1e3))
+for key, n in (("ovlp", 1), ("kin", 1), ("dpm", 3), ("qpm", 6)):
+    print(key, "median %.1f us, min %.1f us" % timeit(lambda: eng.int1e(key, ob, out=buf[:n])))
+eng.close()

@@ -16,7 +16,7 @@ LIB = LIBDIR / "libsympleints_b200.so"
 GENDIR = CSRC / "generated"
 OBJDIR = PKG / "lib" / "obj"
 SOURCES = [CSRC / "si_lib.cu", CSRC / "si_program.cpp"]
-HEADERS = [CSRC / "si_machine.h", CSRC / "si_program.h", PKG.parent / "include" / "sympleints_b200.h"]
+HEADERS = [CSRC / "si_machine.h", CSRC / "si_program.h", CSRC / "si_onee.cuh", PKG.parent / "include" / "sympleints_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -40,8 +40,9 @@ def needs_build():
 
 def generate_sources():
     """Run the code generator (class-specialised 3c2e kernels) into csrc/generated/."""
-    from .codegen import gen3c2e, gencoul
+    from .codegen import gen3c2e, gencoul, genonee
 
+    genonee.write_sources(str(GENDIR))   # header only (included by si_onee.cuh)
     return [Path(f) for f in gen3c2e.write_sources(str(GENDIR))] + \
            [Path(f) for f in gencoul.write_sources(str(GENDIR))]
 
@@ -57,7 +58,7 @@ def _compile_obj(src, obj, verbose):
 
 def build_library(force=False, verbose=False, jobs=None):
     gen = generate_sources()
-    deps = SOURCES + HEADERS + [CSRC / "si_g3.h", PKG / "codegen" / "gen3c2e.py", PKG / "codegen" / "gencoul.py",
+    deps = SOURCES + HEADERS + [CSRC / "si_g3.h", PKG / "codegen" / "gen3c2e.py", PKG / "codegen" / "gencoul.py", PKG / "codegen" / "genonee.py",
                                 GENDIR / "g3_table.inc", GENDIR / "gc_table.inc"] + gen
     for tj in (PKG / "codegen" / "tuning.json", PKG / "codegen" / "tuning_coul.json"):
         if tj.exists():

@@ -31,6 +31,7 @@
 #include "si_program.h"
 #include "generated/g3_table.inc"
 #include "generated/gc_table.inc"
+#include "si_onee.cuh"
 
 // ---------------------------------------------------------------------------
 // device-side data
@@ -411,6 +412,7 @@ struct si_context {
     // shell sets by content: a set created again with identical content re-attaches to the cached object
     // (device arrays are uploaded again, the shell-batcher's pair sets / tuple tables / aux lists are kept)
     std::vector<struct si_basis*> basis_cache;   // least recently used first
+    std::map<size_t, int> onee_occ;              // resident blocks per SM of k_onee by dynamic shared-memory size
 };
 static const size_t SI_BASIS_CACHE = 8;
 
@@ -604,6 +606,8 @@ int si_init(int device, int lmax, int lauxmax, const double* boys_table, int nro
     SI_CUDA(cudaFuncSetAttribute(k_two_index, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     SI_CUDA(cudaFuncSetAttribute(k_coul, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     SI_CUDA(cudaFuncSetAttribute(k_3c2e, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    SI_CUDA(cudaFuncSetAttribute(k_onee<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    SI_CUDA(cudaFuncSetAttribute(k_onee<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     // per-device attribute of every generated kernel (one context per device may live in the same process)
     if (g3_set_attributes(c->max_smem) || gc_set_attributes(c->max_smem)) {
         g_last_error = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for a generated kernel";
@@ -1139,10 +1143,123 @@ static int run_two_index(si_context* c, const si_basis* cb, int key, int sph, in
     return fan.end();
 }
 
+// ovlp / kin / dpm / qpm (dqpm) through the fused kernel k_onee: ONE launch for all shell-pair classes and all
+// requested operators (mask bit c = component c of si_onee.cuh; out[c] its (nbf, nbf) matrix)
+static int run_onee(si_context* c, const si_basis* cb, unsigned mask, double* const* outc, int normalize, const double* R,
+                    cudaStream_t user) {
+    si_basis* b = const_cast<si_basis*>(cb);
+    SI_CUDA(cudaSetDevice(c->device));
+    int rc = build_pair_classes(b);
+    if (rc) return rc;
+    if (b->lmax > c->lmax || b->lmax > ONEE_MAXL) {
+        g_last_error = "basis angular momentum exceeds the context limit for this key";
+        return SI_ERR_LMAX;
+    }
+    std::vector<const si_basis::PairClass*> cls;
+    for (auto& pc : b->full.classes) cls.push_back(&pc);
+    if (cls.size() > 15) return SI_ERR_INTERNAL;
+    // heaviest blocks first
+    std::sort(cls.begin(), cls.end(), [](const si_basis::PairClass* x, const si_basis::PairClass* y) {
+        return si_ncart(x->La) * si_ncart(x->Lb) > si_ncart(y->La) * si_ncart(y->Lb);
+    });
+    // two launches (classes with small / large blocks, see k_onee), concurrent on two streams
+    Fan fan{c, user};
+    fan.limit = 2;
+    rc = fan.begin();
+    if (rc) return rc;
+    for (int big = 1; big >= 0; --big) {
+        OneEArgs A;
+        memset(&A, 0, sizeof(A));
+        int wsz_max = 0, g = 0, ns = 0;
+        for (size_t i = 0; i < cls.size(); ++i) {
+            const int la = cls[i]->La, lb = cls[i]->Lb, tpw = 32 / onee_ept(la, lb);
+            if ((int)onee_is_big(la, lb) != big) continue;
+            A.seg[ns].items = cls[i]->d_items;
+            A.seg[ns].n = cls[i]->n;
+            A.seg[ns].la = la;
+            A.seg[ns].lb = lb;
+            g += (cls[i]->n + tpw - 1) / tpw;
+            A.seg[ns].group_end = g;
+            wsz_max = std::max(wsz_max, onee_wsz(la, lb) * tpw);
+            ++ns;
+        }
+        if (!ns) continue;
+        A.nseg = ns;
+        A.ngroups = g;
+        A.ppair = b->full.d_ppair[normalize == SI_NORM_PGTO ? 1 : 0];
+        A.exps = b->d_exps;
+        A.poff = b->d_poff;
+        for (int d = 0; d < 3; ++d) A.R[d] = R ? R[d] : 0.0;
+        for (int k = 0; k < ONEE_NCOMP; ++k) A.out[k] = ((mask >> k) & 1u) ? outc[k] : nullptr;
+        A.nbf = b->nbf_sph;
+        A.counter = c->d_counters + (c->next_counter++ % SI_NCOUNTERS);
+        const int warps = 4;
+        const size_t smem = (size_t)warps * wsz_max * sizeof(double);
+        // resident blocks per SM for this shared-memory size (cached per context: the occupancy query costs ~10 us of host time)
+        const size_t okey = smem * 2 + big;
+        auto occ_it = c->onee_occ.find(okey);
+        if (occ_it == c->onee_occ.end()) {
+            int occ = 0;
+            cudaError_t e = big ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_onee<4, true>, warps * 32, smem)
+                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_onee<4, false>, warps * 32, smem);
+            if (e != cudaSuccess || occ < 1) occ = 1;
+            occ_it = c->onee_occ.emplace(okey, occ).first;
+        }
+        const int grid = std::max(1, std::min((g + warps - 1) / warps, c->sm_count * occ_it->second));
+        cudaStream_t s;
+        rc = fan.stream(&s);
+        if (rc) return rc;
+        if (big)
+            k_onee<4, true><<<grid, warps * 32, smem, s>>>(A, mask, wsz_max);
+        else
+            k_onee<4, false><<<grid, warps * 32, smem, s>>>(A, mask, wsz_max);
+        c->launches++;
+        SI_CUDA(cudaGetLastError());
+    }
+    return fan.end();
+}
+
+static bool onee_usable(const si_context* c, const si_basis* b, int sph, int normalize) {
+    return sph && normalize != SI_NORM_NONE && !si_env().force_lut && b->lmax <= ONEE_MAXL && b->lmax <= c->lmax;
+}
+
+int si_int1e_set(si_context* c, const si_basis* b, int sph, int normalize, const double* R, double* out_dev, void* stream) {
+    if (!c || !b || !out_dev) return SI_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    const long long nbf = sph ? b->nbf_sph : b->nbf_cart;
+    if (onee_usable(c, b, sph, normalize)) {
+        double* outc[ONEE_NCOMP];
+        for (int k = 0; k < ONEE_NCOMP; ++k) outc[k] = out_dev + (long long)k * nbf * nbf;
+        return mark_done(c, (cudaStream_t)stream, run_onee(c, b, 0x7FFu, outc, normalize, R, (cudaStream_t)stream));
+    }
+    // Cartesian / un-normalised output: the four operators one after the other on the stage machine
+    const int keys[4] = {SI_OVLP, SI_KIN, SI_DPM, SI_QPM}, offs[4] = {0, 1, 2, 5};
+    for (int k = 0; k < 4; ++k) {
+        int rc = run_two_index(c, b, keys[k], sph, normalize, R, 0, nullptr, nullptr, out_dev + (long long)offs[k] * nbf * nbf,
+                               (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return mark_done(c, (cudaStream_t)stream, SI_OK);
+}
+
 int si_int1e(si_context* c, const si_basis* b, int key, int sph, int normalize, const double* R, double* out_dev,
              void* stream) {
     if (!c || !b || !out_dev) return SI_ERR_ARG;
     if (!check_key_2idx(key)) return SI_ERR_KEY;
+    if (onee_usable(c, b, sph, normalize)) {
+        std::lock_guard<std::recursive_mutex> lk1(c->mu);
+        const long long n2 = (long long)b->nbf_sph * b->nbf_sph;
+        double* outc[ONEE_NCOMP] = {nullptr};
+        unsigned mask = 0;
+        switch (key) {
+            case SI_OVLP: mask = 1u; outc[0] = out_dev; break;
+            case SI_KIN: mask = 2u; outc[1] = out_dev; break;
+            case SI_DPM: mask = 0x1Cu; for (int k = 0; k < 3; ++k) outc[2 + k] = out_dev + k * n2; break;
+            case SI_QPM: mask = 0x7E0u; for (int k = 0; k < 6; ++k) outc[5 + k] = out_dev + k * n2; break;
+            default: mask = (1u << 5) | (1u << 8) | (1u << 10); outc[5] = out_dev; outc[8] = out_dev + n2; outc[10] = out_dev + 2 * n2; break;
+        }
+        return mark_done(c, (cudaStream_t)stream, run_onee(c, b, mask, outc, normalize, R, (cudaStream_t)stream));
+    }
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     return mark_done(c, (cudaStream_t)stream,
                      run_two_index(c, b, key, sph, normalize, R, 0, nullptr, nullptr, out_dev, (cudaStream_t)stream));

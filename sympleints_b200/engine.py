@@ -149,6 +149,17 @@ class Engine:
                                     c_void_p(out.data_ptr()), self._stream()))
         return out[0] if ncomp == 1 else out
 
+    def int1e_set(self, basis, sph=True, normalize="cgto", R=(0.0, 0.0, 0.0), out=None):
+        """ovlp, kin, dpm, qpm in one call: (11, nbf, nbf) = [ovlp, kin, dpm x y z, qpm xx xy xz yy yz zz]."""
+        torch = self.torch
+        nbf = basis.nbf(sph)
+        if out is None:
+            out = torch.empty((11, nbf, nbf), dtype=torch.float64, device=self.tdev)
+        Rv = np.ascontiguousarray(R, dtype=np.float64)
+        check(self.lib.si_int1e_set(self.ctx, basis.handle, int(sph), NORMALIZE[normalize], _dp(Rv),
+                                    c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     def int2c2e(self, basis, sph=True, normalize="cgto", out=None):
         return self.int1e("2c2e", basis, sph, normalize, out=out)
 

@@ -35,6 +35,7 @@ SIGNATURES = {
     "si_basis_nshell": (c_int, [c_void_p]),
     "si_basis_packed_rows": (c_longlong, [c_void_p]),
     "si_int1e": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double_p, c_void_p, c_void_p]),
+    "si_int1e_set": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double_p, c_void_p, c_void_p]),
     "si_coul": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double_p, c_double_p, c_void_p, c_void_p]),
     "si_int2c2e": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "si_int3c2e": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),

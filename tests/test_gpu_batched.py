@@ -50,6 +50,27 @@ def test_one_electron_matrices(engine, small, key, sph):
     assert np.array_equal(h, g)
 
 
+@pytest.mark.parametrize("normalize", ["cgto", "pgto"])
+def test_one_electron_set_in_one_launch(engine, small, normalize):
+    """si_int1e_set: ovlp, kin, dpm, qpm of all classes from the fused kernel k_onee (two concurrent launches: the
+    classes with small and with large blocks), against the oracle and bit-identical to the per-key calls (same
+    kernel, operator mask)."""
+    shells, _, _, ob, _ = small
+    R = np.array([0.3, -0.2, 0.5])
+    l0 = engine.launch_count()
+    S = engine.int1e_set(ob, normalize=normalize, R=R)
+    assert engine.launch_count() - l0 <= 2
+    S = S.cpu().numpy()
+    for key, o0, n in (("ovlp", 0, 1), ("kin", 1, 1), ("dpm", 2, 3), ("qpm", 5, 6)):
+        o = oracle_matrix(key, shells, normalize=normalize, R=R)
+        g = S[o0:o0 + n]
+        assert np.abs(g - o).max() <= 1e-14 + 1e-12 * np.abs(o).max(), key
+        single = engine.int1e(key, ob, normalize=normalize, R=R).cpu().numpy().reshape(o.shape)
+        assert np.array_equal(single, g), key
+    dq = engine.int1e("dqpm", ob, normalize=normalize, R=R).cpu().numpy()
+    assert np.array_equal(dq, S[[5, 8, 10]])
+
+
 def test_plumbing_config_ovlp_lmax1(engine):
     """BASELINE config 1: 20-atom s/p shell set, ovlp, against the intor_2c-style driver."""
     shells, _ = synthetic.plumbing_basis()
