@@ -903,13 +903,20 @@ def write_sources(outdir, lmax=4, lauxmax=5, nparts=15):
         # launcher for this part
         src.append("#if !defined(SI_G3_HOST_EMU)")
         src.append(f"int g3_launch_part_{pi}(int id, const G3Args& A, int grid, int block, size_t smem, int max_smem, cudaStream_t s) {{")
+        src.append("    // max_smem < 0: programmatic dependent launch (the kernels trigger their dependents at once, so the next")
+        src.append("    // launch of the stream fills the SMs as this one's blocks retire; the launches are independent of each other)")
+        src.append("    cudaLaunchConfig_t cfg = {};")
+        src.append("    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;")
+        src.append("    cudaLaunchAttribute at[1];")
+        src.append("    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;")
+        src.append("    cfg.attrs = at; cfg.numAttrs = max_smem < 0 ? 1 : 0;")
         src.append("    switch (id) {")
         for c in cl:
             g = gens[c]
             cid = c[0] * 100 + c[1] * 10 + c[2]
-            tk = (f"if (A.tuples) {{ g3_tkernel_{g.name}<<<grid, block, smem, s>>>(A); return 0; }} "
+            tk = (f"if (A.tuples) return cudaLaunchKernelEx(&cfg, g3_tkernel_{g.name}, A) != cudaSuccess; "
                   if g.has_table_variant() else "if (A.tuples) return 1; ")
-            src.append(f"        case {cid}: {{ {tk}g3_kernel_{g.name}<<<grid, block, smem, s>>>(A); return 0; }}")
+            src.append(f"        case {cid}: {{ {tk}return cudaLaunchKernelEx(&cfg, g3_kernel_{g.name}, A) != cudaSuccess; }}")
             table.append((cid, pi, g.EPT, g.TPW, g.WSZ))
         src.append("        default: return 1;")
         src.append("    }")

@@ -162,6 +162,7 @@ static inline int si_g3_warp_max(int v) {
 #define SI_G3_WINIT(ptr, n) (ptr)
 #define SI_G3_GLOBAL(mb) __global__ __launch_bounds__(128, mb)
 #define SI_G3_KERNEL_PROLOGUE              \
+    asm volatile("griddepcontrol.launch_dependents;");   /* see g3_launch_part_*: dependents may start at once */ \
     extern __shared__ double g3_smem[];    \
     const int g3_lane = threadIdx.x & 31, g3_warp = threadIdx.x >> 5;                         \
     const long long g3_first = (long long)blockIdx.x * (blockDim.x >> 5) + g3_warp,            \

@@ -287,10 +287,22 @@ __global__ void __launch_bounds__(256) k_3c2e(SiProg P, SiBoys Bt, BasisDev orb,
 }
 
 // copy the lower triangle of an n x n matrix into the upper one (exact symmetry, as intor_2c mirrors)
-__global__ void k_mirror_lower(double* m, long long n) {
-    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long i = blockIdx.y;
-    if (j < n && j > i) m[i * n + j] = m[j * n + i];
+// upper triangle := transpose of the lower triangle, in 32 x 32 tiles through shared memory (coalesced reads and
+// writes; tiles above the diagonal are written, diagonal tiles only above the diagonal)
+__global__ void __launch_bounds__(256) k_mirror_lower(double* m, long long n) {
+    __shared__ double tile[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;   // tile (bi, bj) of the UPPER part is written: bj >= bi
+    if (bj < bi) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const long long row = (long long)bj * 32 + r, col = (long long)bi * 32 + tx;   // source tile (bj, bi), lower part
+        if (row < n && col < n) tile[r][tx] = m[row * n + col];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const long long row = (long long)bi * 32 + r, col = (long long)bj * 32 + tx;
+        if (row < n && col < n && col > row) m[row * n + col] = tile[tx][r];
+    }
 }
 
 // mode 0: si_boys (the reference's summation order); 1: si_boys_fast, the variant every generated 3c2e kernel
@@ -347,7 +359,10 @@ struct SiEnv {
     bool gc_profile = false, g3_profile = false, force_lut = false, force_fan = false, tuple_tables = true;
     int g3_warps_per_block = 4, g3_grid_per_sm = 4;
     double g3_small_total = 2.0e9, g3_big_flops = 2.5e8;
-    bool pdl = true;
+    int g3_fan = 2;
+    bool graphs = true;
+    int pdl = -1;                    // -1: automatic (calls below g3_pdl_total model flops), 0 / 1: forced
+    double g3_pdl_total = 1.5e11;
     SiEnv() {
         auto geti = [](const char* n, int dflt) { const char* e = getenv(n); return e ? atoi(e) : dflt; };
         auto getd = [](const char* n, double dflt) { const char* e = getenv(n); return e ? atof(e) : dflt; };
@@ -364,7 +379,10 @@ struct SiEnv {
         g3_grid_per_sm = std::max(1, geti("SI_G3_GRID_PER_SM", 4));
         g3_small_total = getd("SI_G3_SMALL_TOTAL", 2.0e9);
         g3_big_flops = getd("SI_G3_BIG_FLOPS", 2.5e8);
-        pdl = getb("SI_G3_PDL", true);
+        pdl = geti("SI_G3_PDL", -1);
+        g3_pdl_total = getd("SI_G3_PDL_TOTAL", 1.5e11);
+        g3_fan = std::max(1, std::min(SI_NSTREAMS, geti("SI_G3_FAN", 2)));
+        graphs = getb("SI_GRAPHS", true);
     }
 };
 static const SiEnv& si_env() {
@@ -413,6 +431,7 @@ struct si_context {
     // (device arrays are uploaded again, the shell-batcher's pair sets / tuple tables / aux lists are kept)
     std::vector<struct si_basis*> basis_cache;   // least recently used first
     std::map<size_t, int> onee_occ;              // resident blocks per SM of k_onee by dynamic shared-memory size
+    bool capturing = false;                      // a call is being captured into a CUDA graph (no ev_last traffic)
 };
 static const size_t SI_BASIS_CACHE = 8;
 
@@ -486,6 +505,17 @@ struct si_basis {
     // 2c2e through the generated 3c2e kernels: (a|b) = (a s0|b) with a unit s shell of exponent 0
     mutable si_basis* twoc_orb = nullptr;     // copy of this basis + the s0 shell (last)
     mutable PairSet* twoc_pairs = nullptr;    // pairs (shell j, s0)
+    // The metric is ~36 short class launches + the mirror kernel: launch-rate bound when issued one by one.  After
+    // a first ordinary call (which fills every cache) the call sequence is captured into a CUDA graph per
+    // (output pointer, normalisation) and replayed with one cudaGraphLaunch.
+    struct TwocGraph {
+        double* out = nullptr;
+        int normalize = 0;
+        cudaGraphExec_t exec = nullptr;
+        int kernels = 0;
+    };
+    mutable std::vector<TwocGraph> twoc_graphs;
+    mutable bool twoc_warm = false;
 };
 
 const char* si_strerror(int status) {
@@ -893,6 +923,7 @@ static void basis_free(si_basis* b) {
         free_pair_set(b->twoc_pairs);
         delete b->twoc_pairs;
     }
+    for (auto& g : b->twoc_graphs) cudaGraphExecDestroy(g.exec);
     if (b->twoc_orb) si_basis_destroy(b->twoc_orb);   // (drops the reference; the object lives in the cache)
     for (auto& r : b->aux_ranges) {
         cudaFree(r.d_list);
@@ -1041,7 +1072,7 @@ struct Fan {
     int begin() {
         memset(used, 0, sizeof(used));
         // order this call after the previous call on this context, whatever stream that one was given
-        if (c->ev_last_valid) SI_CUDA(cudaStreamWaitEvent(user, c->ev_last, 0));
+        if (c->ev_last_valid && !c->capturing) SI_CUDA(cudaStreamWaitEvent(user, c->ev_last, 0));
         SI_CUDA(cudaMemsetAsync(c->d_counters, 0, SI_NCOUNTERS * sizeof(int), user));
         c->next_counter = 0;
         SI_CUDA(cudaEventRecord(c->ev_fork, user));
@@ -1066,8 +1097,10 @@ struct Fan {
                 SI_CUDA(cudaEventRecord(c->ev_join[i], c->streams[i]));
                 SI_CUDA(cudaStreamWaitEvent(user, c->ev_join[i], 0));
             }
-        SI_CUDA(cudaEventRecord(c->ev_last, user));
-        c->ev_last_valid = true;
+        if (!c->capturing) {
+            SI_CUDA(cudaEventRecord(c->ev_last, user));
+            c->ev_last_valid = true;
+        }
         return SI_OK;
     }
 };
@@ -1310,13 +1343,65 @@ int si_int2c2e(si_context* c, const si_basis* b, int sph, int normalize, double*
         b->twoc_pairs = ps;
     }
     const size_t n = (size_t)b->nbf_sph;
-    int rc = int3c2e_impl(c, b->twoc_orb, b, 0, b->nshell, normalize, SI_LAYOUT_PACKED, b->twoc_pairs, out_dev, n * n, stream);
-    if (rc) return rc;
-    dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
-    k_mirror_lower<<<grid, 256, 0, (cudaStream_t)stream>>>(out_dev, (long long)n);
-    c->launches++;
-    SI_CUDA(cudaGetLastError());
-    return mark_done(c, (cudaStream_t)stream, SI_OK);
+    cudaStream_t user = (cudaStream_t)stream;
+    auto enqueue = [&]() -> int {
+        int rc = int3c2e_impl(c, b->twoc_orb, b, 0, b->nshell, normalize, SI_LAYOUT_PACKED, b->twoc_pairs, out_dev, n * n, stream);
+        if (rc) return rc;
+        const unsigned nt = (unsigned)((n + 31) / 32);
+        k_mirror_lower<<<dim3(nt, nt), 256, 0, user>>>(out_dev, (long long)n);
+        c->launches++;
+        SI_CUDA(cudaGetLastError());
+        return SI_OK;
+    };
+    if (!si_env().graphs || !b->twoc_warm || si_env().g3_profile || user == nullptr) {
+        // (the legacy default stream cannot be captured)
+        int rc = enqueue();
+        if (rc == SI_OK) b->twoc_warm = true;
+        return mark_done(c, user, rc);
+    }
+    const si_basis::TwocGraph* tg = nullptr;
+    for (auto& g : b->twoc_graphs)
+        if (g.out == out_dev && g.normalize == normalize) tg = &g;
+    if (!tg) {
+        if (c->ev_last_valid) SI_CUDA(cudaStreamWaitEvent(user, c->ev_last, 0));
+        const long long l0 = c->launches;
+        SI_CUDA(cudaStreamBeginCapture(user, cudaStreamCaptureModeThreadLocal));
+        c->capturing = true;
+        int rc = enqueue();
+        c->capturing = false;
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(user, &graph);
+        const int nk = (int)(c->launches - l0);
+        c->launches = l0;
+        if (rc != SI_OK || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            // capture not possible (e.g. a cache had to be refilled): issue the launches directly
+            rc = enqueue();
+            return mark_done(c, user, rc);
+        }
+        si_basis::TwocGraph g;
+        g.out = out_dev;
+        g.normalize = normalize;
+        g.kernels = nk;
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            g_last_error = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e);
+            return SI_ERR_CUDA;
+        }
+        if (b->twoc_graphs.size() >= 4) {
+            cudaGraphExecDestroy(b->twoc_graphs.front().exec);
+            b->twoc_graphs.erase(b->twoc_graphs.begin());
+        }
+        b->twoc_graphs.push_back(g);
+        tg = &b->twoc_graphs.back();
+    } else if (c->ev_last_valid) {
+        SI_CUDA(cudaStreamWaitEvent(user, c->ev_last, 0));
+    }
+    SI_CUDA(cudaGraphLaunch(tg->exec, user));
+    c->launches += tg->kernels;
+    return mark_done(c, user, SI_OK);
 }
 
 // out[i] += sum_{sp >= 1} part[sp - 1][i] in a fixed order (charge-split partial matrices of the coul kernels)
@@ -1633,7 +1718,6 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
     BasisDev od_orb = basis_dev(orb, 1, normalize);
     BasisDev od_aux = basis_dev(aux, 1, normalize);
     Fan fan{c, user};
-    fan.limit = 2;
     rc = fan.begin();
     if (rc) return rc;
     // heaviest classes first
@@ -1652,11 +1736,18 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
             jobs.push_back({&pc, kv.first, cost});
         }
     std::sort(jobs.begin(), jobs.end(), [](const Job& a, const Job& b) { return a.cost > b.cost; });
+    bool use_pdl = false;
     {
         // a call that is small as a whole (the 2c2e metric, tiny systems) is launch-latency bound: use all streams
         double total = 0.0;
         for (auto& j : jobs) total += j.cost;
-        if (2.0 * total < si_env().g3_small_total) fan.limit = SI_NSTREAMS;
+        // Programmatic dependent launch (one stream, every launch's blocks fill the SMs as the previous launch's
+        // blocks retire) pays when the launches are short, e.g. one rank's shard of 4 or 8: measured 9.36 -> 9.09 ms
+        // for a 1/8 shard, but 65.4 -> 66.1 ms for the whole tensor, where two alternating streams stay the default.
+        use_pdl = si_env().pdl < 0 ? (2.0 * total < si_env().g3_pdl_total && 2.0 * total >= si_env().g3_small_total)
+                                   : si_env().pdl != 0;
+        fan.limit = use_pdl ? 1 : si_env().g3_fan;
+        if (2.0 * total < si_env().g3_small_total && !use_pdl) fan.limit = SI_NSTREAMS;
     }
     for (auto& job : jobs) {
         DevProgram* p;
@@ -1715,7 +1806,7 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
                 fprintf(stderr, "G3PROF %d%d%d %.4f\n", job.pc->La, job.pc->Lb, job.Lc, ms);
                 cudaEventDestroy(e0);
                 cudaEventDestroy(e1);
-            } else if (g3_launch(g3[1], g3[0], ga, grid, block, smem, c->max_smem, s)) return SI_ERR_INTERNAL;
+            } else if (g3_launch(g3[1], g3[0], ga, grid, block, smem, use_pdl ? -1 : c->max_smem, s)) return SI_ERR_INTERNAL;
         } else {
             size_t smem = 0;
             int nw = pick_warps(c, p->dev, 4, &smem);
