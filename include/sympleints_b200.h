@@ -53,6 +53,10 @@ extern "C" {
 #define SI_COUL 5  /* coulomb3d */
 #define SI_2C2E 6  /* int2c2e3d */
 #define SI_3C2E 7  /* int3c2e3d_sph */
+#define SI_GTO 8        /* {cart,sph}_gto3d: f(ax, da, A, R, result), values of the shell's functions at the point R
+                           (sympleints/main.py:520-549, defs/gto.py); si_eval_block ignores the b arguments */
+#define SI_PREFACTOR 9  /* prefactors: da db rP^(a+b), normalised, C2S on both indices (main.py:481-518,
+                           defs/overlap.py:16-34); rP is passed as R (a module-level name in the reference's code) */
 
 /* --normalize (sympleints/main.py:109-114) */
 #define SI_NORM_NONE 0
@@ -101,6 +105,14 @@ int si_basis_nbf(const si_basis* basis, int sph);     /* number of basis functio
 int si_basis_nshell(const si_basis* basis);
 /* number of rows of the packed 3-index layout: sum over shell pairs i>=j of nf_i*nf_j */
 long long si_basis_packed_rows(const si_basis* basis);
+/*
+ * Restrict the shell pairs the device entry points work on to (i, j <= i), shell_begin <= i < shell_end, optionally
+ * without the diagonal pairs: 2-index matrices then receive only those blocks (and their mirror images), the packed
+ * 3-index layout holds only those rows (si_basis_selected_rows).  The per-class micro-benchmark uses it to build pure
+ * same-class batches (the reference's benchmark.py:65-142 times one class at a time); (0, nshell, 0) restores all pairs.
+ */
+int si_basis_select_rows(si_basis* basis, int shell_begin, int shell_end, int skip_diagonal);
+long long si_basis_selected_rows(const si_basis* basis);
 
 /*
  * One-electron matrices over a shell set: out[(comp, mu, nu)], C order, shape (ncomp, nbf, nbf),
@@ -129,6 +141,15 @@ int si_int2c2e(si_context* ctx, const si_basis* aux, int sph, int normalize, dou
  */
 int si_int3c2e(si_context* ctx, const si_basis* orb, const si_basis* aux, int aux_shell_begin,
                int aux_shell_end, int normalize, int layout, double* out_dev, size_t out_len, void* stream);
+
+/*
+ * Shell functions on a grid (the batched form of the `gto` key): out[(mu, g)] = chi_mu(r_g), shape (nbf, npoints),
+ * C order; points_xyz: npoints*3 host doubles.  si_gto: DEVICE output, si_gto_h: host output.
+ */
+int si_gto(si_context* ctx, const si_basis* basis, int sph, int normalize, long long npoints, const double* points_xyz,
+           double* out_dev, void* stream);
+int si_gto_h(si_context* ctx, const si_basis* basis, int sph, int normalize, long long npoints,
+             const double* points_xyz, double* out_host);
 
 /* Host-buffer variants: allocate device scratch, run, copy the result back (synchronous). */
 int si_int1e_h(si_context* ctx, const si_basis* basis, int key, int sph, int normalize, const double* R,

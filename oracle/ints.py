@@ -452,7 +452,9 @@ def _finish(vals, Ls, ncomp, coeffs, exps, sph, normalize):
             out[ci].flat[k] = np.sum(v)
     if sph:
         Cs = [cart2sph(L).astype(dtype) for L in Ls]
-        if len(Ls) == 2:
+        if len(Ls) == 1:
+            out = np.einsum("ia,na->ni", Cs[0], out)
+        elif len(Ls) == 2:
             out = np.einsum("ia,jb,nab->nij", Cs[0], Cs[1], out)
         else:
             out = np.einsum("ia,jb,kc,nabc->nijk", Cs[0], Cs[1], Cs[2], out)
@@ -555,6 +557,27 @@ def int3c2e_sph(La, Lb, Lc, ax, da, A, bx, db, B, cx, dc, C, R=None, normalize="
         for c in canonical_order(Lc)
     ]
     return _finish(vals, (La, Lb, Lc), 1, (da, db, dc), (ax, bx, cx), True, normalize)
+
+
+def gto(La, ax, da, A, R, sph=True, normalize="cgto"):
+    """Values of the shell's functions at the point R (defs/gto.py:9-28, main.py:520-549):
+    sum_k d_k N (R-A)^lmn exp(-a_k |R-A|^2), then lmn/pgto normalisation and C2S."""
+    ax = np.asarray(ax).reshape(-1)
+    da = np.asarray(da).reshape(-1)
+    RA = [R[i] - A[i] for i in range(3)]
+    vals = [RA[0] ** l * np.exp(-ax * RA[0] ** 2) * RA[1] ** m * np.exp(-ax * RA[1] ** 2) * RA[2] ** n * np.exp(-ax * RA[2] ** 2)
+            for (l, m, n) in canonical_order(La)]
+    return _finish(vals, (La,), 1, (da,), (ax,), sph, normalize)
+
+
+def prefactor(La, Lb, ax, da, A, bx, db, B, R=(0.0, 0.0, 0.0), sph=True, normalize="cgto"):
+    """``prefactors`` (defs/overlap.py:16-34, main.py:481-518): da db rP^(a+b) per Cartesian component pair, then
+    normalisation and C2S on both indices.  rP is NOT an argument of the reference's generated functions (they read
+    module-level ``rP`` / ``rP2``); it is passed as R here, with rP2 = rP**2."""
+    ax, da, bx, db = _bc2(ax, da, bx, db)
+    vals = [R[0] ** (a[0] + b[0]) * R[1] ** (a[1] + b[1]) * R[2] ** (a[2] + b[2]) * (ax * 0 + 1.0) * (bx * 0 + 1.0)
+            for a in canonical_order(La) for b in canonical_order(Lb)]
+    return _finish(vals, (La, Lb), 1, (da, db), (ax, bx), sph, normalize)
 
 
 KEY_FUNCS = {

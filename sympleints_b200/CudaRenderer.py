@@ -70,6 +70,9 @@ NAME_TO_KEY = {
     "coulomb3d": "coul",
     "int2c2e3d": "2c2e",
     "int3c2e3d_sph": "3c2e_sph",
+    "sph_gto3d": "gto",        # main.py:520-549 (name = ("sph" if sph else "cart") + "_gto3d")
+    "cart_gto3d": "gto",
+    "prefactors": "prefactor",  # main.py:481-518
 }
 
 _FUNC_TPL = '''
@@ -159,6 +162,8 @@ def batched(shells, aux_shells=None, **kwargs):
     if key == "coul":
         xyz, q = kwargs["charges"]
         return eng.coul(basis, xyz, q, sph=SPHERICAL, normalize=NORMALIZE)
+    if key == "gto":
+        return eng.gto(basis, kwargs["points"], sph=SPHERICAL, normalize=NORMALIZE)
     return eng.int1e(key, basis, sph=SPHERICAL, normalize=NORMALIZE, R=kwargs.get("R", (0.0, 0.0, 0.0)))
 '''
 
@@ -181,9 +186,14 @@ class CudaRenderer(_RefRenderer):
         call_args = list(functions.full_args_for_bf_inds(range(nb))) if hasattr(functions, "full_args_for_bf_inds") else list(args)
         has_R = bool(getattr(functions, "with_ref_center", True))
         names = [a for a in call_args]
+        if has_R and "R" not in names:
+            names.append("R")
         # eval_block(key, Ls, ax, da, A, bx, db, B[, cx, dc, C], R=R)
         prim = names[: 3 * nb]
         call = ", ".join(prim) + (", R=R" if has_R else "")
+        if key == "prefactor":
+            # the reference's generated prefactors read the module-level names rP / rP2 (they are not arguments)
+            call = ", ".join(prim) + ", R=globals()['rP']"
         return _FUNC_TPL.format(fname=name, args=", ".join(names), doc=(doc_str or "").replace('"""', "'''"), key=key,
                                 Ls=tuple(L_tots), call=call, sph=bool(functions.spherical) or key == "3c2e_sph",
                                 normalize=self.normalize)
@@ -225,6 +235,8 @@ class CudaRenderer(_RefRenderer):
         if key in ("2c2e", "3c2e_sph"):
             l_aux = max(max(f.Ls) for f in rendered_funcs)
         l_max = max((max(f.Ls[:2]) for f in rendered_funcs), default=functions.l_max) if key != "2c2e" else 0
+        if key == "gto":
+            l_aux = l_max
         return _MODULE_TPL.format(header=(functions.header or "").replace('"""', "'''"), name=functions.name, key=key,
                                   sph=bool(functions.spherical) or key == "3c2e_sph", normalize=self.normalize,
                                   l_max=l_max, l_aux_max=l_aux, boys=functions.boys_func,
@@ -240,7 +252,8 @@ class CudaRenderer(_RefRenderer):
         return fn
 
 
-def stub_functions(name, l_max, l_aux_max=None, spherical=True, ncomponents=1, boys_func=None, three_center=False):
+def stub_functions(name, l_max, l_aux_max=None, spherical=True, ncomponents=1, boys_func=None, three_center=False,
+                   one_center=False, with_ref_center=True):
     """A ``Functions``-like payload without sympy expressions (duck-typed; see Functions.py:19-37), so that the
     CudaRenderer can be driven without the reference's expression generation."""
     import itertools as it
@@ -250,13 +263,17 @@ def stub_functions(name, l_max, l_aux_max=None, spherical=True, ncomponents=1, b
         classes = [(La, Lb, Lc) for Lb, La in it.combinations_with_replacement(range(l_max + 1), 2)
                    for Lc in range(l_aux_max + 1)]
         args = ["ax", "da", "A", "bx", "db", "B", "cx", "dc", "C", "R"]
+    elif one_center:   # gto: f(ax, da, A, R, result)
+        classes = [(La,) for La in range(l_max + 1)]
+        args = ["ax", "da", "A", "R"]
     else:
         lm = l_max
         classes = [(La, Lb) for Lb, La in it.combinations_with_replacement(range(lm + 1), 2)]
-        args = ["ax", "da", "A", "bx", "db", "B", "R"]
+        args = ["ax", "da", "A", "bx", "db", "B"] + (["R"] if with_ref_center else [])
     ns = SimpleNamespace(name=name, l_max=l_max, l_aux_max=l_aux_max, spherical=spherical, ncomponents=ncomponents,
-                         boys_func=boys_func, hermitian=[0, 1], header="stub Functions payload (no sympy expressions)",
-                         doc_func=lambda Ls: f"class {Ls}", with_ref_center=True, full_args=args,
+                         boys_func=boys_func, hermitian=[] if one_center else [0, 1],
+                         header="stub Functions payload (no sympy expressions)",
+                         doc_func=lambda Ls: f"class {Ls}", with_ref_center=with_ref_center, full_args=args,
                          ls_exprs=[(c, ([], [])) for c in classes])
     ns.full_args_for_bf_inds = lambda inds: args
     return ns

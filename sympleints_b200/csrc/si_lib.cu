@@ -32,6 +32,7 @@
 #include "generated/g3_table.inc"
 #include "generated/gc_table.inc"
 #include "si_onee.cuh"
+#include "si_gto.cuh"
 
 // ---------------------------------------------------------------------------
 // device-side data
@@ -494,6 +495,7 @@ struct si_basis {
     long long row_chunk_bytes = 0;
     int row_chunk_ncol = 0;
     bool pairs_built = false;
+    bool selected = false;    // si_basis_select_rows restricted `full` to a subset of the pairs
     // cached device lists of the aux shells of a range, grouped by angular momentum (3c2e)
     struct AuxRange {
         int sb, se;
@@ -638,6 +640,23 @@ int si_init(int device, int lmax, int lauxmax, const double* boys_table, int nro
     SI_CUDA(cudaFuncSetAttribute(k_3c2e, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     SI_CUDA(cudaFuncSetAttribute(k_onee<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     SI_CUDA(cudaFuncSetAttribute(k_onee<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    {
+        // tables of the gto / prefactor kernels (per device)
+        static SiGtoConst hg;
+        memset(&hg, 0, sizeof(hg));
+        for (int l = 0; l <= SI_GTO_LMAX; ++l) {
+            std::vector<int> lmn;
+            si_cart_order(l, lmn);
+            const std::vector<double> M = si_cart2sph(l), f = si_lmn_factors(l);
+            const int nc = si_ncart(l), ns = si_nsph(l);
+            for (int k = 0; k < nc; ++k) {
+                hg.cart[l][k] = lmn[3 * k] | (lmn[3 * k + 1] << 4) | (lmn[3 * k + 2] << 8);
+                hg.lmn[l][k] = f[k];
+                for (int m = 0; m < ns; ++m) hg.c2s[l][m][k] = M[(size_t)m * nc + k];
+            }
+        }
+        SI_CUDA(cudaMemcpyToSymbol(g_si_gto, &hg, sizeof(hg)));
+    }
     // per-device attribute of every generated kernel (one context per device may live in the same process)
     if (g3_set_attributes(c->max_smem) || gc_set_attributes(c->max_smem)) {
         g_last_error = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for a generated kernel";
@@ -791,6 +810,7 @@ static cudaError_t upload(const std::vector<T>& v, T** d) {
     return e;
 }
 
+static void free_pair_set(si_basis::PairSet* ps);
 int si_basis_create(si_context* c, int nshell, const int* L, const int* nprim, const double* centers,
                     const double* exps, const double* coefs, si_basis** out) {
     if (!c || !out || nshell <= 0 || !L || !nprim || !centers || !exps || !coefs) return SI_ERR_ARG;
@@ -809,6 +829,13 @@ int si_basis_create(si_context* c, int nshell, const int* L, const int* nprim, c
                 memcmp(o->exps.data(), exps, np_ * sizeof(double)) || memcmp(o->coef.data(), coefs, np_ * sizeof(double)))
                 continue;
             if (c->ev_last_valid) SI_CUDA(cudaEventSynchronize(c->ev_last));   // no kernel of an earlier call reads them now
+            if (o->selected && o->users <= 0) {   // a pair selection of an earlier owner does not outlive its handle
+                free_pair_set(&o->full);
+                for (auto& g : o->twoc_graphs) cudaGraphExecDestroy(g.exec);
+                o->twoc_graphs.clear();
+                o->pairs_built = false;
+                o->selected = false;
+            }
             SI_CUDA(cudaMemcpy(o->d_L, L, nshell * sizeof(int), cudaMemcpyHostToDevice));
             SI_CUDA(cudaMemcpy(o->d_nprim, nprim, nshell * sizeof(int), cudaMemcpyHostToDevice));
             SI_CUDA(cudaMemcpy(o->d_cen, centers, 3 * (size_t)nshell * sizeof(double), cudaMemcpyHostToDevice));
@@ -1043,6 +1070,30 @@ static int build_pair_classes(si_basis* b) {
     if (rc) return rc;
     b->pairs_built = true;
     return SI_OK;
+}
+
+// Restrict the shell pairs the batched entry points work on to (i, j <= i) with shell_begin <= i < shell_end
+// (optionally without the diagonal pairs i == j).  Used by the per-class micro-benchmark (pure same-class
+// batches: one shell of La after n shells of Lb) and for row-wise evaluation; (0, nshell, 0) restores the full set.
+int si_basis_select_rows(si_basis* b, int shell_begin, int shell_end, int skip_diagonal) {
+    if (!b || !basis_is_live(b)) return SI_ERR_ARG;
+    if (shell_begin < 0 || shell_end > b->nshell || shell_begin >= shell_end) return SI_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(b->ctx->mu);
+    SI_CUDA(cudaSetDevice(b->ctx->device));
+    SI_CUDA(cudaDeviceSynchronize());
+    free_pair_set(&b->full);
+    for (auto& g : b->twoc_graphs) cudaGraphExecDestroy(g.exec);
+    b->twoc_graphs.clear();
+    b->pairs_built = false;
+    int rc = build_pair_set(b, shell_begin, shell_end, &b->full, skip_diagonal != 0);
+    if (rc) return rc;
+    b->pairs_built = true;
+    b->selected = !(shell_begin == 0 && shell_end == b->nshell && !skip_diagonal);
+    return SI_OK;
+}
+long long si_basis_selected_rows(const si_basis* b) {
+    if (!b) return -1;
+    return b->pairs_built ? b->full.rows : b->packed_rows;
 }
 
 static BasisDev basis_dev(const si_basis* b, int sph, int normalize) {
@@ -1826,6 +1877,42 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
     return rc;
 }
 
+// ---- gto on a grid ------------------------------------------------------------
+int si_gto(si_context* c, const si_basis* b, int sph, int normalize, long long npoints, const double* points_xyz,
+           double* out_dev, void* stream) {
+    if (!c || !b || !points_xyz || !out_dev || npoints <= 0) return SI_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    if (b->lmax > std::max(c->lmax, c->lauxmax) || b->lmax > SI_GTO_LMAX) return SI_ERR_LMAX;
+    SI_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    double* dpts = nullptr;
+    int rc = ctx_scratch(c, (size_t)3 * npoints, s, &dpts);
+    if (rc) return rc;
+    if (c->ev_last_valid) SI_CUDA(cudaStreamWaitEvent(s, c->ev_last, 0));   // the scratch may be in use by an earlier call
+    SI_CUDA(cudaMemcpyAsync(dpts, points_xyz, (size_t)3 * npoints * sizeof(double), cudaMemcpyHostToDevice, s));
+    BasisDev bd = basis_dev(b, sph, normalize);
+    dim3 grid((unsigned)((npoints + 127) / 128), (unsigned)b->nshell);
+    k_gto<<<grid, 128, 0, s>>>(bd, b->nshell, npoints, dpts, sph, normalize != SI_NORM_NONE, out_dev, npoints);
+    c->launches++;
+    SI_CUDA(cudaGetLastError());
+    SI_CUDA(cudaStreamSynchronize(s));   // points_xyz is the caller's host buffer
+    return mark_done(c, s, SI_OK);
+}
+
+int si_gto_h(si_context* c, const si_basis* b, int sph, int normalize, long long npoints, const double* points_xyz,
+             double* out_host) {
+    if (!c || !b || !out_host || npoints <= 0) return SI_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    SI_CUDA(cudaSetDevice(c->device));
+    const size_t n = (size_t)(sph ? b->nbf_sph : b->nbf_cart) * (size_t)npoints;
+    double* d = nullptr;
+    SI_CUDA(cudaMalloc((void**)&d, n * sizeof(double)));
+    int rc = si_gto(c, b, sph, normalize, npoints, points_xyz, d, nullptr);
+    if (rc == SI_OK && cudaMemcpy(out_host, d, n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = SI_ERR_CUDA;
+    cudaFree(d);
+    return rc;
+}
+
 // ---- host-buffer variants ---------------------------------------------------
 static int run_host(si_context* c, size_t n, double* out_host, const std::function<int(double*)>& f) {
     SI_CUDA(cudaSetDevice(c->device));
@@ -2114,9 +2201,42 @@ int si_fp64_peak(si_context* c, double seconds, double* tflops) {
 int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int normalize, int Ka, const double* ax,
                   const double* da, const double* A, int Kb, const double* bx, const double* db, const double* B,
                   int Kc, const double* cx, const double* dc, const double* C, const double* R, double* result) {
-    if (!c || !ax || !da || !A || !bx || !db || !B || !result || Ka <= 0 || Kb <= 0) return SI_ERR_ARG;
-    if (key < 0 || key > SI_3C2E) return SI_ERR_KEY;
+    if (!c || !ax || !da || !A || !result || Ka <= 0) return SI_ERR_ARG;
+    if (key < 0 || key > SI_PREFACTOR) return SI_ERR_KEY;
+    if (key != SI_GTO && (!bx || !db || !B || Kb <= 0)) return SI_ERR_ARG;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
+    if (key == SI_GTO) {
+        // one-index function f(ax, da, A, R, result): a one-shell set evaluated at the single point R
+        if (!R) return SI_ERR_ARG;
+        if (La < 0 || La > c->lmax) return SI_ERR_LMAX;
+        si_basis* ob1 = nullptr;
+        int rc1 = si_basis_create(c, 1, &La, &Ka, A, ax, da, &ob1);
+        if (rc1) return rc1;
+        rc1 = si_gto_h(c, ob1, sph, normalize, 1, R, result);
+        si_basis_destroy(ob1);
+        return rc1;
+    }
+    if (key == SI_PREFACTOR) {
+        if (!R) return SI_ERR_ARG;
+        if (La < 0 || Lb < 0 || La > c->lmax || Lb > c->lmax) return SI_ERR_LMAX;
+        SI_CUDA(cudaSetDevice(c->device));
+        // the reference's functions are primitive ones (scalar da, db); several primitives are summed
+        double sa = 0.0, sb = 0.0;
+        for (int i = 0; i < Ka; ++i)
+            sa += da[i] * (normalize == SI_NORM_PGTO ? std::sqrt(std::pow(2.0, 2 * La + 1.5) * std::pow(ax[i], La + 1.5) / std::pow(SI_PI, 1.5)) : 1.0);
+        for (int i = 0; i < Kb; ++i)
+            sb += db[i] * (normalize == SI_NORM_PGTO ? std::sqrt(std::pow(2.0, 2 * Lb + 1.5) * std::pow(bx[i], Lb + 1.5) / std::pow(SI_PI, 1.5)) : 1.0);
+        const int na = sph ? si_nsph(La) : si_ncart(La), nb = sph ? si_nsph(Lb) : si_ncart(Lb);
+        double* d = nullptr;
+        int rc1 = ctx_scratch(c, (size_t)na * nb, nullptr, &d);
+        if (rc1) return rc1;
+        if (c->ev_last_valid) SI_CUDA(cudaEventSynchronize(c->ev_last));
+        k_prefactor<<<1, 512>>>(La, Lb, sph, normalize != SI_NORM_NONE, sa * sb, R[0], R[1], R[2], d);
+        c->launches++;
+        SI_CUDA(cudaGetLastError());
+        SI_CUDA(cudaMemcpy(result, d, (size_t)na * nb * sizeof(double), cudaMemcpyDeviceToHost));
+        return SI_OK;
+    }
     const bool three = (key == SI_3C2E);
     if (three && (!cx || !dc || !C || Kc <= 0)) return SI_ERR_ARG;
     if (three) sph = 1;

@@ -52,6 +52,12 @@ class Basis:
     def nbf(self, sph=True):
         return self.nbf_sph if sph else self.nbf_cart
 
+    def select_rows(self, shell_begin=0, shell_end=None, skip_diagonal=False):
+        """Restrict the batched entry points to the shell pairs (i, j <= i), shell_begin <= i < shell_end."""
+        check(self.engine.lib.si_basis_select_rows(self.handle, shell_begin, self.nshell if shell_end is None else shell_end,
+                                                   int(skip_diagonal)))
+        self.packed_rows = self.engine.lib.si_basis_selected_rows(self.handle)
+
     def close(self):
         if self.handle is not None:
             if getattr(self.engine, "ctx", None) is not None:   # the context releases its shell sets itself
@@ -178,6 +184,17 @@ class Engine:
         self.torch.cuda.current_stream(self.tdev).synchronize()
         return out
 
+    def gto(self, basis, points, sph=True, normalize="cgto", out=None):
+        """Values of all basis functions on a grid of points: (nbf, npoints) tensor (batched ``gto`` key)."""
+        torch = self.torch
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        nbf = basis.nbf(sph)
+        if out is None:
+            out = torch.empty((nbf, pts.shape[0]), dtype=torch.float64, device=self.tdev)
+        check(self.lib.si_gto(self.ctx, basis.handle, int(sph), NORMALIZE[normalize], pts.shape[0], _dp(pts),
+                              c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     def aux_cols(self, aux, shell_begin, shell_end):
         return int(aux.foff_sph[shell_end] - aux.foff_sph[shell_begin])
 
@@ -232,14 +249,27 @@ class Engine:
                 "copy_wait_s": out[5], "chunks": int(out[6]), "chunk_bytes": int(out[7])}
 
     # -- one block, generated-function signature ------------------------------
-    def eval_block(self, key, Ls, ax, da, A, bx, db, B, cx=None, dc=None, C=None, R=None, result=None,
+    def eval_block(self, key, Ls, ax, da, A, bx=None, db=None, B=None, cx=None, dc=None, C=None, R=None, result=None,
                    sph=True, normalize="cgto"):
         """``f(ax, da, A, bx, db, B[, cx, dc, C], R, result)`` of the generated modules; broadcast-shaped
-        exponent/coefficient arrays are accepted (they are flattened)."""
+        exponent/coefficient arrays are accepted (they are flattened).  ``gto``: ``f(ax, da, A, R, result)`` with
+        ``Ls = (La,)``; ``prefactor``: rP is passed as ``R``."""
         three = KEYS[key] == 7
+        f = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+        if key == "gto":
+            La = Ls[0]
+            ax, da, A, Rv = map(f, (ax, da, A, R))
+            n = (2 * La + 1) if sph else (La + 1) * (La + 2) // 2
+            if result is None:
+                result = np.empty(n)
+            buf = result if (result.dtype == np.float64 and result.flags.c_contiguous and result.size == n) else np.empty(n)
+            check(self.lib.si_eval_block(self.ctx, KEYS[key], La, 0, 0, int(sph), NORMALIZE[normalize], ax.size, _dp(ax),
+                                         _dp(da), _dp(A), 0, None, None, None, 0, None, None, None, _dp(Rv), _dp(buf)))
+            if buf is not result:
+                result[:n] = buf
+            return result
         La, Lb = Ls[0], Ls[1]
         Lc = Ls[2] if three else 0
-        f = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
         ax, da, A, bx, db, B = map(f, (ax, da, A, bx, db, B))
         if three:
             cx, dc, C = map(f, (cx, dc, C))

@@ -12,8 +12,10 @@ import os
 
 LIB_PATH = Path(os.environ.get("SYMPLEINTS_B200_LIB", PKG / "lib" / "libsympleints_b200.so"))
 
-KEYS = {"ovlp": 0, "kin": 1, "dpm": 2, "qpm": 3, "dqpm": 4, "coul": 5, "2c2e": 6, "3c2e_sph": 7, "3c2e": 7}
-NCOMP = {"ovlp": 1, "kin": 1, "dpm": 3, "qpm": 6, "dqpm": 3, "coul": 1, "2c2e": 1, "3c2e_sph": 1, "3c2e": 1}
+KEYS = {"ovlp": 0, "kin": 1, "dpm": 2, "qpm": 3, "dqpm": 4, "coul": 5, "2c2e": 6, "3c2e_sph": 7, "3c2e": 7, "gto": 8,
+        "prefactor": 9}
+NCOMP = {"ovlp": 1, "kin": 1, "dpm": 3, "qpm": 6, "dqpm": 3, "coul": 1, "2c2e": 1, "3c2e_sph": 1, "3c2e": 1, "gto": 1,
+         "prefactor": 1}
 NORMALIZE = {"none": 0, "cgto": 1, "pgto": 2}
 LAYOUT = {"full": 0, "packed": 1}
 
@@ -34,11 +36,15 @@ SIGNATURES = {
     "si_basis_nbf": (c_int, [c_void_p, c_int]),
     "si_basis_nshell": (c_int, [c_void_p]),
     "si_basis_packed_rows": (c_longlong, [c_void_p]),
+    "si_basis_select_rows": (c_int, [c_void_p, c_int, c_int, c_int]),
+    "si_basis_selected_rows": (c_longlong, [c_void_p]),
     "si_int1e": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double_p, c_void_p, c_void_p]),
     "si_int1e_set": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double_p, c_void_p, c_void_p]),
     "si_coul": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double_p, c_double_p, c_void_p, c_void_p]),
     "si_int2c2e": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "si_int3c2e": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "si_gto": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_double_p, c_void_p, c_void_p]),
+    "si_gto_h": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_double_p, c_double_p]),
     "si_int1e_h": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double_p, c_double_p]),
     "si_coul_h": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double_p, c_double_p, c_double_p]),
     "si_int2c2e_h": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double_p]),

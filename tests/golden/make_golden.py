@@ -28,6 +28,7 @@ MODULES = {  # key -> (module file, dict name, ncomp)
     "ovlp": ("ovlp3d", 1), "kin": ("kinetic3d", 1), "dpm": ("dipole3d", 3), "qpm": ("quadrupole3d", 6),
     "dqpm": ("diag_quadrupole3d", 3), "coul": ("coulomb3d", 1), "2c2e": ("int2c2e3d", 1),
     "3c2e": ("int3c2e3d_sph", 1),
+    "gto": ("sph_gto3d", 1), "prefactor": ("prefactors", 1),
 }
 
 
@@ -80,8 +81,8 @@ def rand_shell(rng, L, K, normalize):
     return exps, coeffs, center
 
 
-def make_blocks(variant, keys, lmax, lauxmax, sph, normalize, seed, classes3=None):
-    d = REFDIR / f"ref_{variant}_python"
+def make_blocks(variant, keys, lmax, lauxmax, sph, normalize, seed, classes3=None, refdir=None):
+    d = REFDIR / f"ref_{refdir or variant}_python"
     if not d.exists():
         print("skip", variant, "(not generated)")
         return
@@ -99,6 +100,31 @@ def make_blocks(variant, keys, lmax, lauxmax, sph, normalize, seed, classes3=Non
         fd = getattr(mod, modname)
         three = key == "3c2e"
         lm = lauxmax if key == "2c2e" else lmax
+        if key == "gto":
+            # one-index functions f(ax, da, A, R, result): the values of a shell's functions at the point R
+            for L in range(lmax + 1):
+                for K in (3, 1):
+                    sa = rand_shell(rng, L, K, normalize)
+                    R = sa[2] + rng.uniform(-1.2, 1.2, 3)
+                    res = {}
+                    for tag, dt in (("f64", np.float64), ("f80", np.longdouble)):
+                        c = lambda x: np.asarray(x, dtype=dt)
+                        result = np.zeros(2 * L + 1 if sph else (L + 1) * (L + 2) // 2, dtype=dt)
+                        fd[(L,)](c(sa[0]), c(sa[1]), c(sa[2]), c(R), result)
+                        res[tag] = result
+                    tagname = f"gto_{L}" if K == 3 else f"gto_{L}0"   # (second digit only makes the tag unique)
+                    out[tagname + "_a"] = np.concatenate([sa[0], sa[1], sa[2]])
+                    out[tagname + "_R"] = R
+                    out[tagname + "_ref64"] = res["f64"]
+                    hi = res["f80"].astype(np.float64)
+                    out[tagname + "_ref80hi"] = hi
+                    out[tagname + "_ref80lo"] = (res["f80"] - hi.astype(np.longdouble)).astype(np.float64)
+                    meta.append(tagname)
+                    n += 1
+            continue
+        if key == "prefactor":
+            # the generated functions read the module-level names rP / rP2 (they are not arguments)
+            rP = rng.uniform(-1.5, 1.5, 3)
         if three:
             cls = classes3 or [(a, b, c) for a in range(lmax + 1) for b in range(a + 1) for c in range(lauxmax + 1)]
         else:
@@ -109,7 +135,7 @@ def make_blocks(variant, keys, lmax, lauxmax, sph, normalize, seed, classes3=Non
         for Ls in cls:
             if Ls not in fd:
                 continue
-            Ks = [(3, 2, 2), (1, 1, 1)][n % 2]
+            Ks = [(3, 2, 2), (1, 1, 1)][n % 2] if key != "prefactor" else (1, 1, 1)   # prefactors are primitive functions
             sa = rand_shell(rng, Ls[0], Ks[0], normalize)
             sb = rand_shell(rng, Ls[1], Ks[1], normalize)
             sc = rand_shell(rng, Ls[2], Ks[2], normalize) if three else None
@@ -120,7 +146,12 @@ def make_blocks(variant, keys, lmax, lauxmax, sph, normalize, seed, classes3=Non
             for tag, dt in (("f64", np.float64), ("f80", np.longdouble)):
                 c = lambda x: np.asarray(x, dtype=dt)
                 result = np.zeros(nres, dtype=dt)
-                if three:
+                if key == "prefactor":
+                    mod.rP, mod.rP2 = c(rP), c(rP) ** 2
+                    result = np.zeros(nres, dtype=dt)
+                    fd[Ls](c(sa[0])[0], c(sa[1])[0], c(sa[2]), c(sb[0])[0], c(sb[1])[0], c(sb[2]), result)
+                    R = rP
+                elif three:
                     fd[Ls](c(sa[0])[:, None, None], c(sa[1])[:, None, None], c(sa[2]),
                            c(sb[0])[None, :, None], c(sb[1])[None, :, None], c(sb[2]),
                            c(sc[0])[None, None, :], c(sc[1])[None, None, :], c(sc[2]), c(R), result)
@@ -155,6 +186,9 @@ VARIANTS = {
     "sph_pgto_l2_laux2": dict(keys=["ovlp", "kin", "dpm", "qpm", "coul", "2c2e", "3c2e"], lmax=2, lauxmax=2, sph=True, normalize="pgto", seed=104),
     "sph_none_l2_laux2": dict(keys=["ovlp", "kin", "dpm", "coul", "2c2e", "3c2e"], lmax=2, lauxmax=2, sph=True, normalize="none", seed=105),
     "sph_cgto_l1_laux1": dict(keys=["ovlp", "2c2e", "3c2e"], lmax=1, lauxmax=1, sph=True, normalize="cgto", seed=106),
+    # section 8(f)-1 keys; generated into the same reference directory as the lmax 4 set
+    "sph_cgto_l4_gto_prefactor": dict(keys=["gto", "prefactor"], lmax=4, lauxmax=5, sph=True, normalize="cgto", seed=107,
+                                      refdir="sph_cgto_l4_laux5"),
 }
 
 if __name__ == "__main__":

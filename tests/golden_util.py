@@ -36,7 +36,7 @@ def load_variant(v):
             K = (arr.size - 3) // 2
             return arr[:K], arr[K:2 * K], arr[2 * K:]
 
-        blk = dict(tag=tag, key=key, Ls=Ls, a=split(z[tag + "_a"]), b=split(z[tag + "_b"]),
+        blk = dict(tag=tag, key=key, Ls=Ls, a=split(z[tag + "_a"]), b=split(z[tag + "_b"]) if tag + "_b" in z else None,
                    c=split(z[tag + "_c"]) if tag + "_c" in z else None, R=z[tag + "_R"],
                    ref64=z[tag + "_ref64"],
                    ref80=z[tag + "_ref80hi"].astype(np.longdouble) + z[tag + "_ref80lo"].astype(np.longdouble))
@@ -61,8 +61,12 @@ def oracle_block(blk, sph, normalize, dtype=np.float64):
 
     key, Ls = blk["key"], blk["Ls"]
     c = lambda t: tuple(np.asarray(x, dtype=dtype) for x in t)
-    a, b = c(blk["a"]), c(blk["b"])
+    a, b = c(blk["a"]), (c(blk["b"]) if blk["b"] is not None else None)
     if key == "3c2e":
         return ints.int3c2e_sph(*Ls, *a, *b, *c(blk["c"]), normalize=normalize)
+    if key == "gto":   # one-index function: f(ax, da, A, R)
+        return ints.gto(Ls[0], *a, np.asarray(blk["R"], dtype=dtype), sph=sph, normalize=normalize)
+    if key == "prefactor":   # R carries rP (module-level name in the reference's generated code)
+        return ints.prefactor(Ls[0], Ls[1], *a, *b, R=np.asarray(blk["R"], dtype=dtype), sph=sph, normalize=normalize)
     f = ints.KEY_FUNCS[key][0]
     return f(Ls[0], Ls[1], *a, *b, R=np.asarray(blk["R"], dtype=dtype), sph=sph, normalize=normalize)

@@ -54,8 +54,12 @@ def test_plugs_into_reference_run(tmp_path):
     r = CudaRenderer(normalize="cgto")
     assert isinstance(r, Renderer)
     res = run(l_max=1, l_aux_max=1, sph=True, normalization=Normalization.CGTO, out_dir=str(tmp_path), prefix="t",
-              keys=["ovlp", "dpm", "3c2e_sph"], boys_func="oracle.boys", renderers=[r])
-    assert set(res["cuda"]) == {"ovlp3d", "dipole3d", "int3c2e3d_sph"}
+              keys=["ovlp", "dpm", "3c2e_sph", "gto", "prefactor"], boys_func="oracle.boys", renderers=[r])
+    assert set(res["cuda"]) == {"ovlp3d", "dipole3d", "int3c2e3d_sph", "sph_gto3d", "prefactors"}
+    gmod = _load(Path(res["cuda"]["sph_gto3d"]))
+    assert set(gmod.sph_gto3d) == {(0,), (1,)}
+    pmod = _load(Path(res["cuda"]["prefactors"]))
+    assert set(pmod.prefactors) == {(0, 0), (1, 0), (0, 1), (1, 1)}
     mod = _load(Path(res["cuda"]["int3c2e3d_sph"]))
     assert set(mod.int3c2e3d_sph) == {(a, b, c) for a in range(2) for b in range(2) for c in range(2)}
     assert mod.NORMALIZE == "cgto" and mod.SPHERICAL
@@ -75,3 +79,27 @@ def test_rendered_module_evaluates_on_gpu(tmp_path):
     res = np.empty(3 * 3 * 5)
     mod.dipole3d[(1, 2)](ax[:, None], da[:, None], A, bx[None, :], db[None, :], B, R, res)   # reference call style
     np.testing.assert_allclose(res, ints.dpm(1, 2, ax, da, A, bx, db, B, R=R), rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.gpu
+def test_rendered_gto_and_prefactor_modules(tmp_path):
+    """Section 8(f)-1 keys through the plugin: sph_gto3d[(La,)](ax, da, A, R, result) and
+    prefactors[(La, Lb)](ax, da, A, bx, db, B, result) with the module-level rP of the reference's code."""
+    from oracle import ints
+    from sympleints_b200.CudaRenderer import CudaRenderer, stub_functions
+
+    r = CudaRenderer(normalize="cgto")
+    gmod = _load(r.render_write(stub_functions("sph_gto3d", 3, spherical=True, one_center=True), tmp_path))
+    assert sorted(gmod.sph_gto3d) == [(0,), (1,), (2,), (3,)]
+    rng = np.random.default_rng(1)
+    ax = np.array([2.1, 0.6, 0.2])
+    da = ints.norm_cgto_lmn(np.array([0.3, 0.5, 0.4]), ax, 3)
+    A, R = rng.uniform(-1, 1, 3), rng.uniform(-1, 1, 3)
+    res = np.empty(7)
+    gmod.sph_gto3d[(3,)](ax, da, A, R, res)
+    np.testing.assert_allclose(res, ints.gto(3, ax, da, A, R), rtol=1e-12, atol=1e-14)
+    pmod = _load(r.render_write(stub_functions("prefactors", 2, spherical=True, with_ref_center=False), tmp_path))
+    pmod.rP = rng.uniform(-1, 1, 3)
+    res = np.empty(5 * 3)
+    pmod.prefactors[(2, 1)](1.1, 0.7, A, 0.4, 1.3, A, res)
+    np.testing.assert_allclose(res, ints.prefactor(2, 1, [1.1], [0.7], A, [0.4], [1.3], A, R=pmod.rP), rtol=1e-12, atol=1e-14)

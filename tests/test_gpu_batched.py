@@ -262,3 +262,37 @@ def test_edge_cases_single_shell_and_reversed_order(engine):
     va = engine.coul(engine.basis(shells), np.array([[0.2, 0.1, 0.4], [1.0, -1.0, 0.5]]), np.array([1.0, -0.5])).cpu().numpy()
     vb = engine.coul(engine.basis(rev), np.array([[0.2, 0.1, 0.4], [1.0, -1.0, 0.5]]), np.array([1.0, -0.5])).cpu().numpy()
     assert np.abs(va - vb[np.ix_(perm, perm)]).max() <= 1e-13 * np.abs(va).max()
+
+
+def test_per_class_microbenchmark_and_row_selection(engine):
+    """sympleints_b200.benchmark (counterpart of sympleints/benchmark.py:65-142): pure same-class batches through
+    si_basis_select_rows; the selected blocks agree with the full evaluation and nothing else is written."""
+    from sympleints_b200 import benchmark
+    from sympleints_b200.shells import Shell
+
+    rows = benchmark.run_key(engine, "3c2e_sph", 2, 2, nprims=2, npairs=16, naux=8, reps=2,
+                             classes=[(2, 1, 2), (1, 1, 0), (2, 0, 1)])
+    assert [(r["La"], r["Lb"], r["Lc"]) for r in rows] == [(2, 1, 2), (1, 1, 0), (2, 0, 1)]
+    assert all(r["tot"] > 0 and r["tuples"] == 128 and r["tflops"] > 0 for r in rows)
+    rows = benchmark.run_key(engine, "ovlp", 2, 2, nprims=3, npairs=8, reps=2, classes=[(2, 1, None)])
+    assert rows[0]["integrals"] == 8 * 5 * 3 and rows[0]["tflops"] is None
+    assert "La Lb Lc" in benchmark.format_rows("ovlp", rows)
+    # selection semantics
+    rng = np.random.default_rng(4)
+    shells = [Shell(L, rng.uniform(-2, 2, 3), rng.uniform(0.2, 1, 2), 10 ** rng.uniform(-0.5, 1, 2)) for L in (1, 1, 0, 2)]
+    aux = [Shell(1, rng.uniform(-2, 2, 3), [1.0], [0.9]), Shell(2, rng.uniform(-2, 2, 3), [1.0], [0.5])]
+    b, ab = engine.basis(shells), engine.basis(aux)
+    full = engine.int3c2e(b, ab, layout="full").cpu().numpy()
+    S = engine.int1e("kin", b).cpu().numpy()
+    b.select_rows(3, 4, skip_diagonal=True)          # pairs (d-shell, each of the three earlier shells)
+    assert b.packed_rows == 5 * (3 + 3 + 1)
+    T = engine.int3c2e(b, ab, layout="packed").cpu().numpy()
+    assert np.array_equal(T.reshape(7 * 5, 8)[:15].reshape(5, 3, 8), full[7:12, 0:3])
+    import torch
+    out = torch.full((12, 12), 7.0, dtype=torch.float64, device=engine.tdev)
+    engine.int1e("kin", b, out=out)
+    o = out.cpu().numpy()
+    assert np.array_equal(o[7:12, 0:7], S[7:12, 0:7]) and np.array_equal(o[0:7, 7:12], S[0:7, 7:12])
+    assert (o[0:7, 0:7] == 7.0).all() and (o[7:12, 7:12] == 7.0).all()
+    b.select_rows()                                   # back to all pairs
+    assert np.array_equal(engine.int1e("kin", b).cpu().numpy(), S)

@@ -15,6 +15,8 @@ def _gpu_block(engine, blk, sph, normalize):
     a, b, c = blk["a"], blk["b"], blk["c"]
     if key == "3c2e":
         return engine.eval_block("3c2e", Ls, *a, *b, *c, R=blk["R"], normalize=normalize)
+    if key == "gto":
+        return engine.eval_block("gto", Ls[:1], *a, R=blk["R"], sph=sph, normalize=normalize)
     return engine.eval_block(key, Ls, *a, *b, R=blk["R"], sph=sph, normalize=normalize)
 
 
@@ -116,6 +118,25 @@ def test_blocks_match_reference_golden(engine, variant):
         if not ok:
             bad.append(rep)
     assert not bad, bad[:5]
+
+
+def test_gto_on_a_grid(engine):
+    """Batched form of the gto key: all functions of a shell set on a grid of points, (nbf, npoints)."""
+    from sympleints_b200 import synthetic
+
+    shells, sites = synthetic.orbital_basis(natoms=3, seed=5)
+    rng = np.random.default_rng(8)
+    pts = rng.uniform(-2, 8, (257, 3))
+    for sph, normalize in ((True, "cgto"), (True, "pgto"), (False, "cgto"), (True, "none")):
+        V = engine.gto(engine.basis(shells), pts, sph=sph, normalize=normalize).cpu().numpy()
+        row = 0
+        for s in shells:
+            n = 2 * s.L + 1 if sph else (s.L + 1) * (s.L + 2) // 2
+            for g in (0, 100, 256):
+                o = ints.gto(s.L, s.exps, s.coeffs, s.center, pts[g], sph=sph, normalize=normalize)
+                assert np.abs(V[row:row + n, g] - o).max() <= 1e-14 + 1e-12 * np.abs(o).max()
+            row += n
+        assert row == V.shape[0]
 
 
 def _rand_shell(rng, L, K):
