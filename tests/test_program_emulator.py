@@ -20,6 +20,8 @@ def test_emulated_programs_match_reference_blocks(variant):
     sph, normalize, blocks = gu.load_variant(variant)
     bad = []
     for blk in blocks:
+        if blk["key"] in ("gto", "prefactor"):
+            continue   # closed-form keys with kernels of their own (csrc/si_gto.cuh), not stage programs
         coefs_scaled = blk
         if normalize == "pgto":
             # the C ABI folds the radial pgto norm into the coefficients (si_basis_create);
