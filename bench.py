@@ -618,6 +618,38 @@ def run_ours(args, rank, world, local_rank):
             e2e["parity"] = reduce_parity(parity_3c2e(host_np, shells, aux, my[0], my[1], 1, seed=91 + rank))
         del host
 
+    # ---- on-request all-gather of the sharded tensor (NCCL over NVLink), timed separately: NOT part of `value` ----
+    allgather = None
+    if world > 1 and not args.no_allgather:
+        cols = sdist.shard_columns([2 * s.L + 1 for s in aux], ranges)
+        try:
+            full = torch.empty((ob.packed_rows, cols[-1][1]), dtype=torch.float64, device=eng.tdev)
+            sdist.allgather_slabs(out, cols, out=full)   # warm-up (NCCL channel set-up)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            sdist.allgather_slabs(out, cols, out=full)
+            g1.record()
+            barrier()
+            tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=eng.tdev)
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            # every rank now holds the whole tensor: compare a foreign column block with what its owner computed
+            other = (rank + 1) % world
+            c0, c1 = cols[other]
+            chk = parity_3c2e(full[:, c0:c1], shells, aux, ranges[other][0], ranges[other][1], 1, seed=55 + rank)
+            okv = torch.tensor([chk["failed"]], dtype=torch.float64, device=eng.tdev)
+            dist.all_reduce(okv, op=dist.ReduceOp.SUM)
+            recv = work["bytes"] - mywork["bytes"]
+            allgather = {"ms": float(tg.item()), "bytes_received_per_rank": int(recv),
+                         "GBs_per_rank": recv / (float(tg.item()) * 1e-3) / 1e9,
+                         "how": "dist.all_gather_into_tensor on slabs padded to the widest shard, row-blocked staging, "
+                                "then strided copies into the column ranges (sympleints_b200/dist.py); excluded from value",
+                         "parity_of_received_blocks": {"blocks": chk["blocks"] * world, "failed": int(okv.item())}}
+            del full
+        except Exception as e:   # e.g. out of memory for the full tensor next to the shard
+            allgather = {"unavailable": str(e)[:200]}
+        torch.cuda.empty_cache()
+
     if rank == 0:
         fp64_peak = eng.fp64_peak(0.5)
         peaks = {}
@@ -655,6 +687,7 @@ def run_ours(args, rank, world, local_rank):
                     "parity sample can be judged at 1e-12",
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "parity": parity,
             "shard": {"aux_shell_ranges": ranges, "columns_rank0": ncol},
+            "allgather": allgather,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline_3c2e(
@@ -665,6 +698,7 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line))
         bad = (parity or {}).get("failed", 0) + ((e2e or {}).get("parity") or {}).get("failed", 0)
         bad += sum((v.get("parity") or {}).get("failed", 0) for v in (line.get("other_keys") or {}).values() if isinstance(v, dict))
+        bad += ((allgather or {}).get("parity_of_received_blocks") or {}).get("failed", 0)
     else:
         bad = 0
     eng.close()
@@ -819,6 +853,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-keys", action="store_true", help="skip the 1e set, coul and 2c2e legs (N=1)")
     ap.add_argument("--other-keys", action="store_true", help="(default now; kept for compatibility)")
+    ap.add_argument("--no-allgather", action="store_true", help="skip the separately timed all-gather of the shards (N > 1)")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle check of the timed output")
     ap.add_argument("--no-numba", action="store_true", help="skip the Numba-renderer baseline of the 1e keys")
     ap.add_argument("--numba-worker", action="store_true", help=argparse.SUPPRESS)

@@ -37,12 +37,15 @@ def shard_columns(aux_sizes, ranges):
     return [(int(off[b]), int(off[e])) for (b, e) in ranges]
 
 
-def allgather_slabs(local_slab, col_ranges, group=None):
+def allgather_slabs(local_slab, col_ranges, group=None, out=None, row_block=None):
     """Assemble the full (rows, naux) tensor on every rank from the per-rank (rows, ncol_r) slabs.
 
-    Slabs have unequal widths, so each rank's slab is broadcast from its owner into the matching
-    column range (one collective per rank; with NCCL these are NVLink broadcasts).  Used only on
-    request -- the scaling benchmark never calls it."""
+    The slabs are column blocks of different widths of a row-major matrix, so they are not contiguous in the
+    result.  Each rank's slab is padded to the widest one and ONE ``all_gather_into_tensor`` (NCCL all-gather over
+    NVLink / NVSwitch; gloo in the CPU tests) moves a block of rows from all ranks at once; the blocks are then
+    copied into their column ranges.  ``row_block`` bounds the staging buffer (world x row_block x wmax doubles;
+    default: at most ~2 GiB).  Used only on request -- the scaling benchmark times it separately, outside the
+    scaling figure."""
     import torch
     import torch.distributed as dist
 
@@ -50,10 +53,19 @@ def allgather_slabs(local_slab, col_ranges, group=None):
     rank = dist.get_rank(group)
     rows = local_slab.shape[0]
     ncol = col_ranges[-1][1]
-    full = torch.empty((rows, ncol), dtype=local_slab.dtype, device=local_slab.device)
-    for r in range(world):
-        c0, c1 = col_ranges[r]
-        buf = local_slab.contiguous() if r == rank else torch.empty((rows, c1 - c0), dtype=local_slab.dtype, device=local_slab.device)
-        dist.broadcast(buf, src=r, group=group)
-        full[:, c0:c1] = buf
+    wmax = max(c1 - c0 for (c0, c1) in col_ranges)
+    assert local_slab.shape[1] == col_ranges[rank][1] - col_ranges[rank][0]
+    full = out if out is not None else torch.empty((rows, ncol), dtype=local_slab.dtype, device=local_slab.device)
+    if row_block is None:
+        row_block = max(1, min(rows, (1 << 28) // max(1, world * wmax)))
+    send = torch.zeros((row_block, wmax), dtype=local_slab.dtype, device=local_slab.device)
+    recv = torch.empty((world, row_block, wmax), dtype=local_slab.dtype, device=local_slab.device)
+    w_me = local_slab.shape[1]
+    for r0 in range(0, rows, row_block):
+        n = min(row_block, rows - r0)
+        send[:n, :w_me] = local_slab[r0:r0 + n]
+        dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
+        for r in range(world):
+            c0, c1 = col_ranges[r]
+            full[r0:r0 + n, c0:c1] = recv[r, :n, :c1 - c0]
     return full

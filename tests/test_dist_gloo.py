@@ -49,7 +49,8 @@ def _worker(rank, world, port, rows, sizes, ranges, q):
     g = torch.Generator().manual_seed(7)
     ref = torch.rand((rows, cols[-1][1]), generator=g, dtype=torch.float64)   # same on both ranks
     full = sdist.allgather_slabs(ref[:, c0:c1].clone(), cols)
-    q.put((rank, bool(torch.equal(full, ref))))
+    blocked = sdist.allgather_slabs(ref[:, c0:c1].clone(), cols, row_block=5)   # several all-gathers + a ragged tail
+    q.put((rank, bool(torch.equal(full, ref)) and bool(torch.equal(blocked, ref))))
     dist.destroy_process_group()
 
 
