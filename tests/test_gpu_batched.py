@@ -296,3 +296,59 @@ def test_per_class_microbenchmark_and_row_selection(engine):
     assert (o[0:7, 0:7] == 7.0).all() and (o[7:12, 7:12] == 7.0).all()
     b.select_rows()                                   # back to all pairs
     assert np.array_equal(engine.int1e("kin", b).cpu().numpy(), S)
+
+
+def test_entry_points_from_two_host_threads(engine, oracle_table):
+    """The C ABI from several host threads (the reference's functions are pure / nogil): two contexts
+    used concurrently, and ONE context shared by two threads that pass different CUDA streams (calls on a
+    context are serialised by its mutex and ordered on the device through its completion event)."""
+    import threading
+
+    import torch
+
+    import sympleints_b200
+
+    shells_a, sites = synthetic.orbital_basis(natoms=3, seed=21)
+    shells_b, _ = synthetic.orbital_basis(natoms=2, seed=22)
+    aux = synthetic.aux_basis(sites, seed=23)
+    ref = {}
+    for name, sh in (("a", shells_a), ("b", shells_b)):
+        b = engine.basis(sh)
+        ref[name] = (engine.int1e("kin", b).cpu().numpy(), engine.int1e("qpm", b, R=(0.1, 0.2, 0.3)).cpu().numpy())
+    ref3 = engine.int3c2e(engine.basis(shells_a), engine.basis(aux), layout="packed").cpu().numpy()
+    errors = []
+
+    def worker(eng, name, sh, with_3c):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                b = eng.basis(sh)
+                ab = eng.basis(aux) if with_3c else None
+                for _ in range(10):
+                    k = eng.int1e("kin", b)
+                    q = eng.int1e("qpm", b, R=(0.1, 0.2, 0.3))
+                    t = eng.int3c2e(b, ab, layout="packed") if with_3c else None
+                    st.synchronize()
+                    if not (np.array_equal(k.cpu().numpy(), ref[name][0]) and np.array_equal(q.cpu().numpy(), ref[name][1])):
+                        errors.append((name, "2-index result differs"))
+                    if with_3c and not np.array_equal(t.cpu().numpy(), ref3):
+                        errors.append((name, "3-index result differs"))
+        except Exception as e:   # noqa: BLE001
+            errors.append((name, repr(e)))
+
+    # (1) two contexts, one thread each
+    e1 = sympleints_b200.get_engine(0, 4, 5, boys_table=oracle_table)
+    e2 = sympleints_b200.get_engine(0, 4, 5, boys_table=oracle_table)
+    th = [threading.Thread(target=worker, args=(e1, "a", shells_a, True)),
+          threading.Thread(target=worker, args=(e2, "b", shells_b, False))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    e1.close()
+    e2.close()
+    assert not errors, errors[:3]
+    # (2) one context shared by two threads on different streams
+    th = [threading.Thread(target=worker, args=(engine, "a", shells_a, True)),
+          threading.Thread(target=worker, args=(engine, "b", shells_b, False))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors[:3]
