@@ -55,6 +55,8 @@ extern "C" {
 #define SI_3C2E 7  /* int3c2e3d_sph */
 #define SI_GTO 8        /* {cart,sph}_gto3d: f(ax, da, A, R, result), values of the shell's functions at the point R
                            (sympleints/main.py:520-549, defs/gto.py); si_eval_block ignores the b arguments */
+#define SI_MULTI_SPH 10 /* multipole3d_sph: 9 components R_lm, l <= 2, m = -l..l, about the centre P of every primitive
+                           pair (sympleints/defs/multipole.py:60-138, main.py:752-800); spherical + normalised output only */
 #define SI_PREFACTOR 9  /* prefactors: da db rP^(a+b), normalised, C2S on both indices (main.py:481-518,
                            defs/overlap.py:16-34); rP is passed as R (a module-level name in the reference's code) */
 
@@ -116,7 +118,7 @@ long long si_basis_selected_rows(const si_basis* basis);
 
 /*
  * One-electron matrices over a shell set: out[(comp, mu, nu)], C order, shape (ncomp, nbf, nbf),
- * both triangles filled (what intor_2c returns).  key in {SI_OVLP, SI_KIN, SI_DPM, SI_QPM, SI_DQPM}.
+ * both triangles filled (what intor_2c returns).  key in {SI_OVLP, SI_KIN, SI_DPM, SI_QPM, SI_DQPM, SI_MULTI_SPH}.
  * R: multipole origin (3 doubles, host).  out is a DEVICE pointer; stream is a cudaStream_t (may be NULL).
  */
 int si_int1e(si_context* ctx, const si_basis* basis, int key, int sph, int normalize, const double* R,

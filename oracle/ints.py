@@ -580,6 +580,43 @@ def prefactor(La, Lb, ax, da, A, bx, db, B, R=(0.0, 0.0, 0.0), sph=True, normali
     return _finish(vals, (La, Lb), 1, (da, db), (ax, bx), sph, normalize)
 
 
+# real regular solid harmonics R_lm, l <= 2, m = -l..l, as polynomials in (x, y, z): {exponents: coefficient}
+# (sympleints/sym_solid_harmonics.py Rlm_polys_up_to_l_iter(2, order=mOrder.NATURAL), evaluated once)
+_SQ3 = sqrt(3.0)
+RLM_POLYS = [
+    {(0, 0, 0): 1.0},
+    {(0, 1, 0): 1.0}, {(0, 0, 1): 1.0}, {(1, 0, 0): 1.0},
+    {(1, 1, 0): _SQ3}, {(0, 1, 1): _SQ3}, {(2, 0, 0): -0.5, (0, 2, 0): -0.5, (0, 0, 2): 1.0}, {(1, 0, 1): _SQ3},
+    {(2, 0, 0): 0.5 * _SQ3, (0, 2, 0): -0.5 * _SQ3},
+]
+
+
+def multi_sph(La, Lb, ax, da, A, bx, db, B, R=None, sph=True, normalize="cgto"):
+    """``multipole3d_sph`` (defs/multipole.py:60-138, main.py:752-800): integrals over the nine spherical multipole
+    operators R_lm, l <= 2, about the centre P = (aA + bB)/(a + b) of EVERY primitive pair; operators of order
+    l > La + Lb are set to zero as the reference does (multipole.py:118-121).  Primitive functions in the reference;
+    several primitives are summed here, each pair with its own origin."""
+    ax, da, bx, db = _bc2(ax, da, bx, db)
+    A = [A[i] for i in range(3)]
+    B = [B[i] for i in range(3)]
+    pr = _Pair(ax, A, bx, B, R=None)
+    pr.PR = [0.0 * pr.P[i] for i in range(3)]     # origin = P of each primitive pair
+    m1 = [_Multipole1d(pr, d) for d in range(3)]
+    vals = []
+    for poly in RLM_POLYS:
+        order = sum(next(iter(poly)))
+        for a in canonical_order(La):
+            for b in canonical_order(Lb):
+                if order > La + Lb:
+                    vals.append(0.0 * ax * bx)
+                    continue
+                v = 0.0
+                for Le, coef in poly.items():
+                    v = v + coef * m1[0](a[0], b[0], Le[0]) * m1[1](a[1], b[1], Le[1]) * m1[2](a[2], b[2], Le[2])
+                vals.append(v)
+    return _finish(vals, (La, Lb), 9, (da, db), (ax, bx), sph, normalize)
+
+
 KEY_FUNCS = {
     "ovlp": (ovlp, 1),
     "kin": (kin, 1),
@@ -588,4 +625,5 @@ KEY_FUNCS = {
     "dqpm": (dqpm, 3),
     "coul": (coul, 1),
     "2c2e": (int2c2e, 1),
+    "multi_sph": (multi_sph, 9),
 }

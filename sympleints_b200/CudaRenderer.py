@@ -73,6 +73,7 @@ NAME_TO_KEY = {
     "sph_gto3d": "gto",        # main.py:520-549 (name = ("sph" if sph else "cart") + "_gto3d")
     "cart_gto3d": "gto",
     "prefactors": "prefactor",  # main.py:481-518
+    "multipole3d_sph": "multi_sph",  # main.py:752-800
 }
 
 _FUNC_TPL = '''

@@ -1230,7 +1230,7 @@ static int run_two_index(si_context* c, const si_basis* cb, int key, int sph, in
 // ovlp / kin / dpm / qpm (dqpm) through the fused kernel k_onee: ONE launch for all shell-pair classes and all
 // requested operators (mask bit c = component c of si_onee.cuh; out[c] its (nbf, nbf) matrix)
 static int run_onee(si_context* c, const si_basis* cb, unsigned mask, double* const* outc, int normalize, const double* R,
-                    cudaStream_t user) {
+                    cudaStream_t user, int origin_p = 0) {
     si_basis* b = const_cast<si_basis*>(cb);
     SI_CUDA(cudaSetDevice(c->device));
     int rc = build_pair_classes(b);
@@ -1274,6 +1274,7 @@ static int run_onee(si_context* c, const si_basis* cb, unsigned mask, double* co
         A.exps = b->d_exps;
         A.poff = b->d_poff;
         for (int d = 0; d < 3; ++d) A.R[d] = R ? R[d] : 0.0;
+        A.origin_p = origin_p;
         for (int k = 0; k < ONEE_NCOMP; ++k) A.out[k] = ((mask >> k) & 1u) ? outc[k] : nullptr;
         A.nbf = b->nbf_sph;
         A.counter = c->d_counters + (c->next_counter++ % SI_NCOUNTERS);
@@ -1326,9 +1327,69 @@ int si_int1e_set(si_context* c, const si_basis* b, int sph, int normalize, const
     return mark_done(c, (cudaStream_t)stream, SI_OK);
 }
 
+// multipole3d_sph: the nine real regular solid harmonic operators R_lm, l <= 2, m = -l..l (coefficients of
+// sympleints/sym_solid_harmonics.py, natural m order) from the ten Cartesian multipoles 1, x..z, xx..zz about P
+__global__ void k_multi_sph_combine(const double* cart11, double* out9, long long n2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    const double s3 = 1.7320508075688772;
+    const double S = cart11[i], x = cart11[2 * n2 + i], y = cart11[3 * n2 + i], z = cart11[4 * n2 + i];
+    const double xx = cart11[5 * n2 + i], xy = cart11[6 * n2 + i], xz = cart11[7 * n2 + i], yy = cart11[8 * n2 + i],
+                 yz = cart11[9 * n2 + i], zz = cart11[10 * n2 + i];
+    out9[i] = S;
+    out9[n2 + i] = y;
+    out9[2 * n2 + i] = z;
+    out9[3 * n2 + i] = x;
+    out9[4 * n2 + i] = s3 * xy;
+    out9[5 * n2 + i] = s3 * yz;
+    out9[6 * n2 + i] = zz - 0.5 * (xx + yy);
+    out9[7 * n2 + i] = s3 * xz;
+    out9[8 * n2 + i] = 0.5 * s3 * (xx - yy);
+}
+
+// per shell block: operators of order l > La + Lb are set to zero, as the reference does (defs/multipole.py:118-121)
+__global__ void k_multi_sph_truncate(double* out9, long long nbf, const int* shell_of_fn, const int* L) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbf * nbf) return;
+    const int lsum = L[shell_of_fn[i / nbf]] + L[shell_of_fn[i % nbf]];
+    if (lsum < 1)
+        for (int c = 1; c < 4; ++c) out9[c * nbf * nbf + i] = 0.0;
+    if (lsum < 2)
+        for (int c = 4; c < 9; ++c) out9[c * nbf * nbf + i] = 0.0;
+}
+
 int si_int1e(si_context* c, const si_basis* b, int key, int sph, int normalize, const double* R, double* out_dev,
              void* stream) {
     if (!c || !b || !out_dev) return SI_ERR_ARG;
+    if (key == SI_MULTI_SPH) {
+        // (sph + cgto|pgto only: served by the fused kernel with the origin at P of every primitive pair)
+        if (!onee_usable(c, b, sph, normalize)) {
+            g_last_error = "multi_sph is available for spherical, normalised output only";
+            return SI_ERR_KEY;
+        }
+        std::lock_guard<std::recursive_mutex> lk1(c->mu);
+        cudaStream_t s = (cudaStream_t)stream;
+        const long long nbf = b->nbf_sph, n2 = nbf * nbf;
+        double* scr = nullptr;
+        int rc = ctx_scratch(c, (size_t)11 * n2 + (size_t)nbf, s, &scr);
+        if (rc) return rc;
+        double* outc[ONEE_NCOMP];
+        for (int k = 0; k < ONEE_NCOMP; ++k) outc[k] = scr + (long long)k * n2;
+        rc = run_onee(c, b, 0x7FDu, outc, normalize, nullptr, s, 1);
+        if (rc) return rc;
+        k_multi_sph_combine<<<(unsigned)((n2 + 255) / 256), 256, 0, s>>>(scr, out_dev, n2);
+        // shell of every function (uploaded next to the Cartesian scratch)
+        std::vector<int> sof((size_t)nbf);
+        for (int sh = 0; sh < b->nshell; ++sh)
+            for (int m = 0; m < si_nsph(b->L[sh]); ++m) sof[(size_t)b->foff_sph[sh] + m] = sh;
+        int* d_sof = reinterpret_cast<int*>(scr + (size_t)11 * n2);
+        SI_CUDA(cudaMemcpyAsync(d_sof, sof.data(), (size_t)nbf * sizeof(int), cudaMemcpyHostToDevice, s));
+        k_multi_sph_truncate<<<(unsigned)((n2 + 255) / 256), 256, 0, s>>>(out_dev, nbf, d_sof, b->d_L);
+        c->launches += 2;
+        SI_CUDA(cudaGetLastError());
+        SI_CUDA(cudaStreamSynchronize(s));   // `sof` is a host temporary
+        return mark_done(c, s, SI_OK);
+    }
     if (!check_key_2idx(key)) return SI_ERR_KEY;
     if (onee_usable(c, b, sph, normalize)) {
         std::lock_guard<std::recursive_mutex> lk1(c->mu);
@@ -1934,10 +1995,10 @@ static int run_host(si_context* c, size_t n, double* out_host, const std::functi
 
 int si_int1e_h(si_context* c, const si_basis* b, int key, int sph, int normalize, const double* R, double* out) {
     if (!c || !b || !out) return SI_ERR_ARG;
-    if (!check_key_2idx(key)) return SI_ERR_KEY;
+    if (!check_key_2idx(key) && key != SI_MULTI_SPH) return SI_ERR_KEY;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     size_t nbf = sph ? b->nbf_sph : b->nbf_cart;
-    return run_host(c, nbf * nbf * si_ncomp(key), out,
+    return run_host(c, nbf * nbf * (key == SI_MULTI_SPH ? 9 : si_ncomp(key)), out,
                     [&](double* d) { return si_int1e(c, b, key, sph, normalize, R, d, nullptr); });
 }
 int si_coul_h(si_context* c, const si_basis* b, int sph, int normalize, int ncharge, const double* xyz,
@@ -2202,7 +2263,7 @@ int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int n
                   const double* da, const double* A, int Kb, const double* bx, const double* db, const double* B,
                   int Kc, const double* cx, const double* dc, const double* C, const double* R, double* result) {
     if (!c || !ax || !da || !A || !result || Ka <= 0) return SI_ERR_ARG;
-    if (key < 0 || key > SI_PREFACTOR) return SI_ERR_KEY;
+    if (key < 0 || key > SI_MULTI_SPH) return SI_ERR_KEY;
     if (key != SI_GTO && (!bx || !db || !B || Kb <= 0)) return SI_ERR_ARG;
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (key == SI_GTO) {
@@ -2215,6 +2276,36 @@ int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int n
         rc1 = si_gto_h(c, ob1, sph, normalize, 1, R, result);
         si_basis_destroy(ob1);
         return rc1;
+    }
+    if (key == SI_MULTI_SPH) {
+        if (La < 0 || Lb < 0 || La > c->lmax || Lb > c->lmax) return SI_ERR_LMAX;
+        SI_CUDA(cudaSetDevice(c->device));
+        int Ls2[2] = {La, Lb}, nps2[2] = {Ka, Kb};
+        std::vector<double> cen2(6), ex2, co2;
+        for (int d = 0; d < 3; ++d) {
+            cen2[d] = A[d];
+            cen2[3 + d] = B[d];
+        }
+        ex2.insert(ex2.end(), ax, ax + Ka);
+        ex2.insert(ex2.end(), bx, bx + Kb);
+        co2.insert(co2.end(), da, da + Ka);
+        co2.insert(co2.end(), db, db + Kb);
+        si_basis* ob2 = nullptr;
+        int rc2 = si_basis_create(c, 2, Ls2, nps2, cen2.data(), ex2.data(), co2.data(), &ob2);
+        if (rc2) return rc2;
+        const int na = si_nsph(La), nb = si_nsph(Lb), nbf = na + nb;
+        double* d9 = nullptr;
+        rc2 = cudaMalloc((void**)&d9, (size_t)9 * nbf * nbf * sizeof(double)) == cudaSuccess ? SI_OK : SI_ERR_CUDA;
+        if (rc2 == SI_OK) rc2 = si_int1e(c, ob2, SI_MULTI_SPH, sph, normalize, nullptr, d9, nullptr);
+        std::vector<double> h((size_t)9 * nbf * nbf);
+        if (rc2 == SI_OK && cudaMemcpy(h.data(), d9, h.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc2 = SI_ERR_CUDA;
+        cudaFree(d9);
+        si_basis_destroy(ob2);
+        if (rc2) return rc2;
+        for (int q = 0; q < 9; ++q)
+            for (int ia = 0; ia < na; ++ia)
+                for (int jb = 0; jb < nb; ++jb) result[((size_t)q * na + ia) * nb + jb] = h[((size_t)q * nbf + ia) * nbf + na + jb];
+        return SI_OK;
     }
     if (key == SI_PREFACTOR) {
         if (!R) return SI_ERR_ARG;

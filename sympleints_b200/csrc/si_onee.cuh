@@ -41,6 +41,7 @@ struct OneEArgs {
     const double* exps;       // primitive exponents of the shell set
     const int* poff;          // first primitive of every shell
     double R[3];              // multipole origin
+    int origin_p;             // 1: the origin is the centre P of every primitive pair (multi_sph), R unused
     double* out[ONEE_NCOMP];  // (nbf, nbf) matrices, null = operator not requested
     long long nbf;
     int* counter;
@@ -211,7 +212,7 @@ __device__ void onee_body(const OneEArgs& A, const OneEClassSeg& sg, int grp_in_
             // (pi/p)^(3/2) exp(-mu AB^2) da db in the x table, 1 in y and z; pairs with fewer primitives add zeros
             const double base = d == 0 ? (live ? pp[8] : 0.0) * (SI_PI * oop) * sqrt(SI_PI * oop) : 1.0;
             if (q < 3) {
-                onee_multipole_tables<LA, LB>(TB + d * DS, e_hi, base, PA, PB, pp[2 + d] - A.R[d], oo2p);
+                onee_multipole_tables<LA, LB>(TB + d * DS, e_hi, base, PA, PB, A.origin_p ? 0.0 : pp[2 + d] - A.R[d], oo2p);
             } else if (kin) {
                 onee_kinetic_table<LA, LB>(TB + d * DS + 3 * TS, TB + d * DS + 4 * TS, base, PA, PB, oo2p, pp[9], pp[10], oop);
             }

@@ -13,9 +13,9 @@ import os
 LIB_PATH = Path(os.environ.get("SYMPLEINTS_B200_LIB", PKG / "lib" / "libsympleints_b200.so"))
 
 KEYS = {"ovlp": 0, "kin": 1, "dpm": 2, "qpm": 3, "dqpm": 4, "coul": 5, "2c2e": 6, "3c2e_sph": 7, "3c2e": 7, "gto": 8,
-        "prefactor": 9}
+        "prefactor": 9, "multi_sph": 10}
 NCOMP = {"ovlp": 1, "kin": 1, "dpm": 3, "qpm": 6, "dqpm": 3, "coul": 1, "2c2e": 1, "3c2e_sph": 1, "3c2e": 1, "gto": 1,
-         "prefactor": 1}
+         "prefactor": 1, "multi_sph": 9}
 NORMALIZE = {"none": 0, "cgto": 1, "pgto": 2}
 LAYOUT = {"full": 0, "packed": 1}
 

@@ -28,7 +28,7 @@ MODULES = {  # key -> (module file, dict name, ncomp)
     "ovlp": ("ovlp3d", 1), "kin": ("kinetic3d", 1), "dpm": ("dipole3d", 3), "qpm": ("quadrupole3d", 6),
     "dqpm": ("diag_quadrupole3d", 3), "coul": ("coulomb3d", 1), "2c2e": ("int2c2e3d", 1),
     "3c2e": ("int3c2e3d_sph", 1),
-    "gto": ("sph_gto3d", 1), "prefactor": ("prefactors", 1),
+    "gto": ("sph_gto3d", 1), "prefactor": ("prefactors", 1), "multi_sph": ("multipole3d_sph", 9),
 }
 
 
@@ -135,7 +135,7 @@ def make_blocks(variant, keys, lmax, lauxmax, sph, normalize, seed, classes3=Non
         for Ls in cls:
             if Ls not in fd:
                 continue
-            Ks = [(3, 2, 2), (1, 1, 1)][n % 2] if key != "prefactor" else (1, 1, 1)   # prefactors are primitive functions
+            Ks = [(3, 2, 2), (1, 1, 1)][n % 2] if key not in ("prefactor", "multi_sph") else (1, 1, 1)   # primitive functions
             sa = rand_shell(rng, Ls[0], Ks[0], normalize)
             sb = rand_shell(rng, Ls[1], Ks[1], normalize)
             sc = rand_shell(rng, Ls[2], Ks[2], normalize) if three else None
@@ -146,7 +146,10 @@ def make_blocks(variant, keys, lmax, lauxmax, sph, normalize, seed, classes3=Non
             for tag, dt in (("f64", np.float64), ("f80", np.longdouble)):
                 c = lambda x: np.asarray(x, dtype=dt)
                 result = np.zeros(nres, dtype=dt)
-                if key == "prefactor":
+                if key == "multi_sph":   # primitive functions: scalar exponents / coefficients, plain assignments
+                    result = np.zeros(nres, dtype=dt)
+                    fd[Ls](c(sa[0])[0], c(sa[1])[0], c(sa[2]), c(sb[0])[0], c(sb[1])[0], c(sb[2]), c(R), result)
+                elif key == "prefactor":
                     mod.rP, mod.rP2 = c(rP), c(rP) ** 2
                     result = np.zeros(nres, dtype=dt)
                     fd[Ls](c(sa[0])[0], c(sa[1])[0], c(sa[2]), c(sb[0])[0], c(sb[1])[0], c(sb[2]), result)
@@ -189,6 +192,8 @@ VARIANTS = {
     # section 8(f)-1 keys; generated into the same reference directory as the lmax 4 set
     "sph_cgto_l4_gto_prefactor": dict(keys=["gto", "prefactor"], lmax=4, lauxmax=5, sph=True, normalize="cgto", seed=107,
                                       refdir="sph_cgto_l4_laux5"),
+    "sph_cgto_l2_multi_sph": dict(keys=["multi_sph"], lmax=2, lauxmax=2, sph=True, normalize="cgto", seed=108,
+                                  refdir="sph_cgto_l2_laux2"),
 }
 
 if __name__ == "__main__":

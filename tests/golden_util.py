@@ -68,5 +68,7 @@ def oracle_block(blk, sph, normalize, dtype=np.float64):
         return ints.gto(Ls[0], *a, np.asarray(blk["R"], dtype=dtype), sph=sph, normalize=normalize)
     if key == "prefactor":   # R carries rP (module-level name in the reference's generated code)
         return ints.prefactor(Ls[0], Ls[1], *a, *b, R=np.asarray(blk["R"], dtype=dtype), sph=sph, normalize=normalize)
+    if key == "multi_sph":   # origin = centre of every primitive pair, R unused
+        return ints.multi_sph(Ls[0], Ls[1], *a, *b, sph=sph, normalize=normalize)
     f = ints.KEY_FUNCS[key][0]
     return f(Ls[0], Ls[1], *a, *b, R=np.asarray(blk["R"], dtype=dtype), sph=sph, normalize=normalize)

@@ -71,6 +71,19 @@ def test_one_electron_set_in_one_launch(engine, small, normalize):
     assert np.array_equal(dq, S[[5, 8, 10]])
 
 
+def test_spherical_multipoles_about_the_primitive_pair_centres(engine, small):
+    """multi_sph (section 8f-3): the nine R_lm operators, origin = P of every primitive pair, orders above La + Lb
+    zeroed as in the reference (defs/multipole.py:60-138)."""
+    shells, _, _, ob, _ = small
+    g = engine.int1e("multi_sph", ob).cpu().numpy()
+    o = oracle_matrix("multi_sph", shells)
+    assert g.shape == o.shape == (9, ob.nbf_sph, ob.nbf_sph)
+    assert np.abs(g - o).max() <= 1e-14 + 1e-12 * np.abs(o).max()
+    assert np.array_equal(engine.int1e_host("multi_sph", ob), g)
+    with pytest.raises(Exception):
+        engine.int1e("multi_sph", ob, sph=False)
+
+
 def test_plumbing_config_ovlp_lmax1(engine):
     """BASELINE config 1: 20-atom s/p shell set, ovlp, against the intor_2c-style driver."""
     shells, _ = synthetic.plumbing_basis()
