@@ -162,6 +162,14 @@ int si_int2c2e_h(si_context* ctx, const si_basis* aux, int sph, int normalize, d
 int si_int3c2e_h(si_context* ctx, const si_basis* orb, const si_basis* aux, int aux_shell_begin,
                  int aux_shell_end, int normalize, int layout, double* out_host, size_t out_len);
 
+/*
+ * Opt-in primitive pre-screening of the 3c2e kernels (eps = 0 switches it off; that is the default, the parity mode and
+ * the benchmark mode -- the reference's own estimate, graphs/templates/int_3c2e_func.tpl:46-54, is a no-op `continue`).
+ * A primitive triple is skipped when prefactor^2 * min(1, pi / (4 T)) <= eps^2 for all tuples of a warp, i.e. when the
+ * bound of its (ss|s)-type base integral [2 pi^2.5 / (p c sqrt(p+c)) K_ab d_a d_b d_c F_0(T)] is below eps.
+ */
+int si_set_screening(si_context* ctx, double eps);
+
 /* Timing of the last si_int3c2e_h call on this context, seconds: out[0] total, [1] host shell-batcher (0 when the
  * row-chunk pair sets were cached), [2] staging allocation (0 when large enough), [3] host time to enqueue the chunks,
  * [4] device time of the compute chunks, [5] wait for D2H copies after the last kernel, [6] chunks, [7] bytes per chunk. */

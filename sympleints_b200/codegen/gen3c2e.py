@@ -573,6 +573,8 @@ class ClassGen:
         E("const double T = rho * r2pc;")
         E("// 2 pi^2.5 / (sqrt(p+c) p c) * K_ab * d_c ;  1/sqrt(p+c) = sqrt(p+c) / (p+c)")
         E("const double pref = 2.0 * SI_PI_25 * rs_ * oop * ocx * Kab * dc;")
+        E("// opt-in pre-screening: bound of the squared (ss|s)-type base integral, F_0(T)^2 <= min(1, pi / (4 T)); warp-uniform")
+        E("if (A.screen_eps2 > 0.0 && si_g3_warp_all(pref * pref * fmin(1.0, 0.78539816339744831 / fmax(T, 1e-300)) <= A.screen_eps2)) continue;")
         E("const double oo2p = 0.5 * oop, c2 = -0.5 * oop * rho_p;")
         E("const double beta = 0.5 * rpc;      // (rho/c)/(2p)")
         E("const double binv = 2.0 * pc_;")

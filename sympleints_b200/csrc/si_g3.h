@@ -66,6 +66,10 @@ struct G3Args {
     long long ngroups;    // npairs * groups_per_pair, or the number of groups listed in `tuples`
     const int2* tuples;   // optional explicit tuple table: ngroups x tuples-per-warp entries (pair, aux), -1 = padding
     int chunk;            // unused (the kernels request one group per atomic); kept for ABI stability of the struct
+    // opt-in primitive pre-screening (0 = off, the parity / benchmark mode): a primitive triple is skipped when the
+    // square of its (ss|s)-type base integral bound is <= screen_eps2 for every tuple of the warp -- the pPRE2
+    // estimate of sympleints/graphs/templates/int_3c2e_func.tpl:46-54 (a no-op `continue` in the reference)
+    double screen_eps2;
     OutDesc od;
     int* counter;
     SiBoys boys;
@@ -147,6 +151,14 @@ static inline long long si_g3_bcast_group(int v) {
     si_g3_syncwarp();
     return r;
 }
+static inline bool si_g3_warp_all(bool p) {
+    si_g3_emu_warp->xchg[si_g3_emu_lane] = p ? 1 : 0;
+    si_g3_syncwarp();
+    bool a = true;
+    for (int i = 0; i < 32; ++i) a = a && si_g3_emu_warp->xchg[i] != 0;
+    si_g3_syncwarp();
+    return a;
+}
 static inline int si_g3_warp_max(int v) {
     si_g3_emu_warp->xchg[si_g3_emu_lane] = v;
     si_g3_syncwarp();
@@ -197,6 +209,7 @@ __device__ __forceinline__ int si_g3_tri_row(int ai) {
     return (int)((__fsqrt_rn(8.0f * (float)ai + 1.0f) - 1.0f) * 0.5f);
 }
 __device__ __forceinline__ int si_g3_warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ bool si_g3_warp_all(bool p) { return __all_sync(0xffffffffu, p) != 0; }
 #endif
 
 // addressing of the elements (ia = 0..nsa-1, jb, m) of the (a_sph, b_sph, c_sph) block of pair item `it`:

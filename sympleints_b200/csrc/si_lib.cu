@@ -433,6 +433,7 @@ struct si_context {
     std::vector<struct si_basis*> basis_cache;   // least recently used first
     std::map<size_t, int> onee_occ;              // resident blocks per SM of k_onee by dynamic shared-memory size
     bool capturing = false;                      // a call is being captured into a CUDA graph (no ev_last traffic)
+    double screen_eps = 0.0;                     // opt-in primitive pre-screening threshold of the 3c2e kernels (0 = off)
 };
 static const size_t SI_BASIS_CACHE = 8;
 
@@ -1694,6 +1695,7 @@ static void g3_fill_args(G3Args& ga, si_context* c, const BasisDev& orb, const B
     ga.ngroups = (long long)npairs * ga.groups_per_pair;
     ga.tuples = nullptr;
     ga.chunk = 1;
+    ga.screen_eps2 = c->screen_eps * c->screen_eps;
     ga.od = od;
     ga.counter = counter;
     ga.boys = c->boys_dev;
@@ -2199,6 +2201,13 @@ int si_int3c2e_h(si_context* c, const si_basis* corb, const si_basis* aux, int s
     c->breakdown[6] = (double)nchunks;
     c->breakdown[7] = (double)stage_bytes;
     return rc;
+}
+
+int si_set_screening(si_context* c, double eps) {
+    if (!c || !(eps >= 0.0)) return SI_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    c->screen_eps = eps;
+    return SI_OK;
 }
 
 int si_host_breakdown(const si_context* c, double* out8) {

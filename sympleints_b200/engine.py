@@ -241,6 +241,10 @@ class Engine:
                                     _dp(out), out.size))
         return out
 
+    def set_screening(self, eps):
+        """Opt-in primitive pre-screening of the 3c2e kernels (0 = off = parity / benchmark mode)."""
+        check(self.lib.si_set_screening(self.ctx, float(eps)))
+
     def host_breakdown(self):
         """Timing of the last ``int3c2e_host`` call (si_host_breakdown)."""
         out = np.zeros(8)

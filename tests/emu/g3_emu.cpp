@@ -125,6 +125,7 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
         args.ngroups = (long long)(table.size() / cls->tpw);
     }
     args.chunk = 2;
+    args.screen_eps2 = 0.0;
     const int na = 2 * La + 1, nb = 2 * Lb + 1, nc = 2 * Lc + 1;
     // full layout of a 2-shell orbital basis: (nbf, nbf, naux*nc); we extract the (a, b) block afterwards
     const int nbf = na + nb + (npairs == 2 ? na : 0);

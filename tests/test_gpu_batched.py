@@ -365,3 +365,32 @@ def test_entry_points_from_two_host_threads(engine, oracle_table):
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errors, errors[:3]
+
+
+def test_opt_in_primitive_prescreening(engine, small):
+    """si_set_screening: off by default (bit-identical), a tiny threshold changes nothing measurable, a generous one
+    drops only contributions of that size (pPRE2 estimate of graphs/templates/int_3c2e_func.tpl:46-54)."""
+    _, _, _, ob, ab = small
+    ref = engine.int3c2e(ob, ab, layout="packed").cpu().numpy()
+    try:
+        engine.set_screening(1e-30)
+        assert np.abs(engine.int3c2e(ob, ab, layout="packed").cpu().numpy() - ref).max() <= 1e-25
+        engine.set_screening(1e-9)
+        dev = np.abs(engine.int3c2e(ob, ab, layout="packed").cpu().numpy() - ref).max()
+        assert dev <= 1e-6 * np.abs(ref).max()
+    finally:
+        engine.set_screening(0.0)
+    assert np.array_equal(engine.int3c2e(ob, ab, layout="packed").cpu().numpy(), ref)
+
+
+def test_density_fitting_consumers(engine, small):
+    """B = (ab|P) L^-T with (P|Q) = L L^T reproduces (ab|P)(P|Q)^-1(Q|cd) (sympleints_b200/df.py)."""
+    from sympleints_b200 import df
+
+    _, _, _, ob, ab = small
+    T = engine.int3c2e(ob, ab, layout="packed").cpu().numpy()
+    M = engine.int2c2e(ab).cpu().numpy()
+    B = df.fitted_tensor(engine, ob, ab).cpu().numpy()
+    want = T @ np.linalg.solve(M, T.T)
+    got = B @ B.T
+    assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
