@@ -2344,151 +2344,136 @@ int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int n
     if (La < 0 || Lb < 0 || La > lim || Lb > lim || (three && (Lc < 0 || Lc > c->lauxmax))) return SI_ERR_LMAX;
     SI_CUDA(cudaSetDevice(c->device));
     const bool swap = La < Lb;
-    // orbital "basis" of two shells (a = higher L first)
-    int Ls[2] = {swap ? Lb : La, swap ? La : Lb};
-    int nps[2] = {swap ? Kb : Ka, swap ? Ka : Kb};
-    std::vector<double> cen(6), ex, co;
+    // two-shell orbital set (a = higher L first) and one-shell auxiliary set, packed into ONE host image that is
+    // uploaded with a single copy into a context-owned device scratch: one upload, one launch, one read-back per block
+    const int Ls[2] = {swap ? Lb : La, swap ? La : Lb};
+    const int nps[2] = {swap ? Kb : Ka, swap ? Ka : Kb};
     const double* A_ = swap ? B : A;
     const double* B_ = swap ? A : B;
-    for (int d = 0; d < 3; ++d) {
-        cen[d] = A_[d];
-        cen[3 + d] = B_[d];
-    }
-    ex.insert(ex.end(), swap ? bx : ax, (swap ? bx : ax) + nps[0]);
-    ex.insert(ex.end(), swap ? ax : bx, (swap ? ax : bx) + nps[1]);
-    co.insert(co.end(), swap ? db : da, (swap ? db : da) + nps[0]);
-    co.insert(co.end(), swap ? da : db, (swap ? da : db) + nps[1]);
-    si_basis* ob = nullptr;
-    int rc = si_basis_create(c, 2, Ls, nps, cen.data(), ex.data(), co.data(), &ob);
-    if (rc) return rc;
-    si_basis* xb = nullptr;
-    if (three) {
-        rc = si_basis_create(c, 1, &Lc, &Kc, C, cx, dc, &xb);
-        if (rc) {
-            si_basis_destroy(ob);
-            return rc;
-        }
-    }
+    const double* ex_[2] = {swap ? bx : ax, swap ? ax : bx};
+    const double* co_[2] = {swap ? db : da, swap ? da : db};
     DevProgram* p;
-    rc = get_program(c, key, Ls[0], Ls[1], three ? Lc : 0, sph, normalize, &p);
-    if (rc) {
-        si_basis_destroy(ob);
-        if (xb) si_basis_destroy(xb);
-        return rc;
-    }
+    int rc = get_program(c, key, Ls[0], Ls[1], three ? Lc : 0, sph, normalize, &p);
+    if (rc) return rc;
     const SiProg& P = p->dev;
     const int n = P.out_n0 * P.out_n1 * P.nb_total;
-    double* d_out = nullptr;
+    size_t smem = 0;
+    const int nw = pick_warps(c, P, 1, &smem);
+    if (nw < 1) return SI_ERR_INTERNAL;
+    const int npo = nps[0] + nps[1], npc = three ? Kc : 0, npair = nps[0] * nps[1];
+    auto pgto = [&](double a, int l) {
+        return normalize == SI_NORM_PGTO ? std::sqrt(std::pow(2.0, 2 * l + 1.5) * std::pow(a, l + 1.5) / std::pow(SI_PI, 1.5)) : 1.0;
+    };
+    // image layout (doubles): [ints: 16 slots][cen_o 6][ex_o][co_o][cen_a 3][ex_a][co_a][oex_a][pp 9*npair][R 3][q 1]
+    //                         [pair item 8][aux item 6][list + counter 1][out n]
+    size_t o = 0;
+    auto take = [&](size_t nd) { size_t r = o; o += nd; return r; };
+    const size_t o_int = take(8), o_ceno = take(6), o_exo = take(npo), o_coo = take(npo), o_cena = take(3), o_exa = take(npc),
+                 o_coa = take(npc), o_oexa = take(npc), o_pp = take((size_t)9 * npair), o_R = take(3), o_q = take(1),
+                 o_item = take(sizeof(SiPairItem) / 8), o_aitem = take(sizeof(SiAuxItem) / 8), o_cnt = take(1), o_out = take(n);
+    std::vector<double> img(o, 0.0);
+    int* hi = reinterpret_cast<int*>(&img[o_int]);   // L[2] nprim[2] poff[2] | aux: L nprim poff
+    hi[0] = Ls[0]; hi[1] = Ls[1]; hi[2] = nps[0]; hi[3] = nps[1]; hi[4] = 0; hi[5] = nps[0];
+    hi[8] = Lc; hi[9] = npc; hi[10] = 0;
+    for (int d = 0; d < 3; ++d) {
+        img[o_ceno + d] = A_[d];
+        img[o_ceno + 3 + d] = B_[d];
+        if (three) img[o_cena + d] = C[d];
+        img[o_R + d] = R ? R[d] : 0.0;
+    }
+    img[o_q] = 1.0;
+    for (int sh = 0, k = 0; sh < 2; ++sh)
+        for (int i = 0; i < nps[sh]; ++i, ++k) {
+            img[o_exo + k] = ex_[sh][i];
+            img[o_coo + k] = co_[sh][i] * pgto(ex_[sh][i], Ls[sh]);
+        }
+    for (int i = 0; i < npc; ++i) {
+        img[o_exa + i] = cx[i];
+        img[o_coa + i] = dc[i] * pgto(cx[i], Lc);
+        img[o_oexa + i] = 1.0 / cx[i];
+    }
+    for (int i = 0; i < nps[0]; ++i)   // primitive-pair data of the single (a = shell 0, b = shell 1) item
+        for (int j = 0; j < nps[1]; ++j) {
+            double* q = &img[o_pp + ((size_t)i * nps[1] + j) * 9];
+            const double ax_ = ex_[0][i], bx_ = ex_[1][j];
+            const double p_ = ax_ + bx_, oop = 1.0 / p_, mu = ax_ * bx_ * oop;
+            double r2 = 0.0;
+            q[0] = p_;
+            q[1] = oop;
+            for (int d = 0; d < 3; ++d) {
+                q[2 + d] = (ax_ * A_[d] + bx_ * B_[d]) * oop;
+                q[5 + d] = q[2 + d] - A_[d];
+                r2 += (A_[d] - B_[d]) * (A_[d] - B_[d]);
+            }
+            q[8] = std::exp(-mu * r2) * img[o_coo + i] * img[o_coo + nps[0] + j];
+        }
     SiPairItem item;
     memset(&item, 0, sizeof(item));
     item.sa = 0;
     item.sb = 1;
-    SiPairItem* d_item = nullptr;
-    int* d_counter = nullptr;
-    double *d_R = nullptr, *d_q = nullptr;
-    cudaError_t e = cudaMalloc((void**)&d_out, n * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_item, sizeof(item));
-    if (e == cudaSuccess) e = cudaMemcpy(d_item, &item, sizeof(item), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_counter, sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(d_counter, 0, sizeof(int));
+    item.Ka = nps[0];
+    item.Kb = nps[1];
+    for (int d = 0; d < 3; ++d) item.AB[d] = A_[d] - B_[d];
+    memcpy(&img[o_item], &item, sizeof(item));
+    SiAuxItem aitem;
+    memset(&aitem, 0, sizeof(aitem));
+    aitem.Kc = npc;
+    if (three)
+        for (int d = 0; d < 3; ++d) aitem.C[d] = C[d];
+    memcpy(&img[o_aitem], &aitem, sizeof(aitem));
+    if (c->ev_last_valid) SI_CUDA(cudaEventSynchronize(c->ev_last));   // the scratch may still be read by an earlier call
+    double* dimg = nullptr;
+    rc = ctx_scratch(c, img.size(), nullptr, &dimg);
+    if (rc) return rc;
+    SI_CUDA(cudaMemcpy(dimg, img.data(), (img.size() - n) * sizeof(double), cudaMemcpyHostToDevice));
+    SI_CUDA(cudaDeviceSynchronize());   // pageable upload landed before a kernel on any stream reads it
+    const int* di = reinterpret_cast<const int*>(dimg + o_int);
+    BasisDev bd, ad;
+    bd.L = di;
+    bd.nprim = di + 2;
+    bd.poff = di + 4;
+    bd.foff = nullptr;
+    bd.cen = dimg + o_ceno;
+    bd.exps = dimg + o_exo;
+    bd.coef = dimg + o_coo;
+    ad.L = di + 8;
+    ad.nprim = di + 9;
+    ad.poff = di + 10;
+    ad.foff = nullptr;
+    ad.cen = dimg + o_cena;
+    ad.exps = dimg + o_exa;
+    ad.coef = dimg + o_coa;
+    const SiPairItem* d_item = reinterpret_cast<const SiPairItem*>(dimg + o_item);
+    const SiAuxItem* d_aitem = reinterpret_cast<const SiAuxItem*>(dimg + o_aitem);
+    int* d_counter = reinterpret_cast<int*>(dimg + o_cnt);
     OutDesc od;
-    od.out = d_out;
+    od.out = dimg + o_out;
     od.ld = 0;
     od.comp_stride = 0;
     od.nbf = 0;
     od.mode = STORE_BLOCK;
-    size_t smem = 0;
-    int nw = pick_warps(c, P, 1, &smem);
-    if (e == cudaSuccess && nw >= 1) {
-        BasisDev bd = basis_dev(ob, sph, normalize);
-        bd.foff = nullptr;
-        if (three) {
-            BasisDev ad = basis_dev(xb, 1, normalize);
-            const int* g3 = g3_find(Ls[0], Ls[1], Lc);
-            if (g3 && normalize != SI_NORM_NONE && !g3_disabled()) {
-                int zero = 0, *d_list1 = nullptr;
-                e = cudaMalloc((void**)&d_list1, sizeof(int));
-                if (e == cudaSuccess) e = cudaMemcpy(d_list1, &zero, sizeof(int), cudaMemcpyHostToDevice);
-                G3Args ga;
-                // primitive-pair data of the single (a = shell 0, b = shell 1) item
-                std::vector<double> pp((size_t)nps[0] * nps[1] * 9);
-                {
-                    const std::vector<double>& co = (normalize == SI_NORM_PGTO) ? ob->coef_pgto : ob->coef;
-                    for (int i = 0; i < nps[0]; ++i)
-                        for (int j = 0; j < nps[1]; ++j) {
-                            double* q = &pp[((size_t)i * nps[1] + j) * 9];
-                            const double ax_ = ob->exps[i], bx_ = ob->exps[nps[0] + j];
-                            const double p_ = ax_ + bx_, oop = 1.0 / p_, mu = ax_ * bx_ * oop;
-                            double r2 = 0.0;
-                            q[0] = p_;
-                            q[1] = oop;
-                            for (int d = 0; d < 3; ++d) {
-                                q[2 + d] = (ax_ * A_[d] + bx_ * B_[d]) * oop;
-                                q[5 + d] = q[2 + d] - A_[d];
-                                r2 += (A_[d] - B_[d]) * (A_[d] - B_[d]);
-                            }
-                            q[8] = std::exp(-mu * r2) * co[i] * co[nps[0] + j];
-                        }
-                }
-                double* d_pp = nullptr;
-                if (e == cudaSuccess) e = cudaMalloc((void**)&d_pp, pp.size() * sizeof(double));
-                if (e == cudaSuccess) e = cudaMemcpy(d_pp, pp.data(), pp.size() * sizeof(double), cudaMemcpyHostToDevice);
-                item.ppoff = 0;
-                item.Ka = nps[0];
-                item.Kb = nps[1];
-                item.fa0 = 0;
-                item.fb0 = 0;
-                for (int d = 0; d < 3; ++d) item.AB[d] = A_[d] - B_[d];
-                if (e == cudaSuccess) e = cudaMemcpy(d_item, &item, sizeof(item), cudaMemcpyHostToDevice);
-                SiAuxItem aitem;
-                memset(&aitem, 0, sizeof(aitem));
-                aitem.shell = 0;
-                aitem.Kc = Kc;
-                aitem.pc0 = 0;
-                aitem.foff = 0;
-                for (int d = 0; d < 3; ++d) aitem.C[d] = C[d];
-                SiAuxItem* d_aitem = nullptr;
-                if (e == cudaSuccess) e = cudaMalloc((void**)&d_aitem, sizeof(aitem));
-                if (e == cudaSuccess) e = cudaMemcpy(d_aitem, &aitem, sizeof(aitem), cudaMemcpyHostToDevice);
-                g3_fill_args(ga, c, bd, ad, xb->d_oexp, d_item, d_pp, 1, d_list1, d_aitem, 1, 0, od, d_counter, g3[3]);
-                int grid, block;
-                size_t sm2;
-                if (e == cudaSuccess && g3_config(c, g3, ga.ngroups, &grid, &block, &sm2) &&
-                    g3_launch(g3[1], g3[0], ga, 1, 32, (size_t)g3[4] * g3[3] * sizeof(double), c->max_smem, 0))
-                    e = cudaErrorInvalidDeviceFunction;
-                if (e == cudaSuccess) e = cudaDeviceSynchronize();
-                cudaFree(d_list1);
-                cudaFree(d_pp);
-                cudaFree(d_aitem);
-            } else {
-                k_3c2e<<<1, 32, smem>>>(P, c->boys_dev, bd, ad, d_item, 1, nullptr, 1, 0, od, d_counter);
-            }
-        } else if (key == SI_COUL) {
-            double one = 1.0;
-            double Rz[3] = {R ? R[0] : 0.0, R ? R[1] : 0.0, R ? R[2] : 0.0};
-            e = cudaMalloc((void**)&d_R, 3 * sizeof(double));
-            if (e == cudaSuccess) e = cudaMalloc((void**)&d_q, sizeof(double));
-            if (e == cudaSuccess) e = cudaMemcpy(d_R, Rz, 3 * sizeof(double), cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = cudaMemcpy(d_q, &one, sizeof(double), cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) k_coul<<<1, 32, smem>>>(P, c->boys_dev, bd, d_item, 1, d_R, d_q, 1, od);
+    cudaError_t e = cudaSuccess;
+    if (three) {
+        const int* g3 = g3_find(Ls[0], Ls[1], Lc);
+        if (g3 && normalize != SI_NORM_NONE && !g3_disabled()) {
+            G3Args ga;
+            g3_fill_args(ga, c, bd, ad, dimg + o_oexa, d_item, dimg + o_pp, 1, reinterpret_cast<const int*>(dimg + o_cnt) + 1,
+                         d_aitem, 1, 0, od, d_counter, g3[3]);
+            if (g3_launch(g3[1], g3[0], ga, 1, 32, (size_t)g3[4] * g3[3] * sizeof(double), c->max_smem, 0))
+                e = cudaErrorInvalidDeviceFunction;
         } else {
-            k_two_index<<<1, 32, smem>>>(P, c->boys_dev, bd, d_item, 1, key == SI_2C2E ? 1 : 0, R ? R[0] : 0.0,
-                                         R ? R[1] : 0.0, R ? R[2] : 0.0, od, d_counter);
+            k_3c2e<<<1, 32, smem>>>(P, c->boys_dev, bd, ad, d_item, 1, nullptr, 1, 0, od, d_counter);
         }
-        c->launches++;
-        if (e == cudaSuccess) e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    } else if (key == SI_COUL) {
+        k_coul<<<1, 32, smem>>>(P, c->boys_dev, bd, d_item, 1, dimg + o_R, dimg + o_q, 1, od);
+    } else {
+        k_two_index<<<1, 32, smem>>>(P, c->boys_dev, bd, d_item, 1, key == SI_2C2E ? 1 : 0, R ? R[0] : 0.0, R ? R[1] : 0.0,
+                                     R ? R[2] : 0.0, od, d_counter);
     }
+    c->launches++;
+    if (e == cudaSuccess) e = cudaGetLastError();
     std::vector<double> tmp(n);
-    if (e == cudaSuccess) e = cudaMemcpy(tmp.data(), d_out, n * sizeof(double), cudaMemcpyDeviceToHost);
-    cudaFree(d_out);
-    cudaFree(d_item);
-    cudaFree(d_counter);
-    cudaFree(d_R);
-    cudaFree(d_q);
-    si_basis_destroy(ob);
-    if (xb) si_basis_destroy(xb);
-    if (nw < 1) return SI_ERR_INTERNAL;
+    if (e == cudaSuccess) e = cudaMemcpy(tmp.data(), dimg + o_out, n * sizeof(double), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) {
         g_last_error = cudaGetErrorString(e);
         return SI_ERR_CUDA;
