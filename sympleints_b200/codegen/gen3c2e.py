@@ -502,7 +502,7 @@ class ClassGen:
         self.open("for (int ia = 0; ia < Ka; ++ia)")
         self.open("for (int ib = 0; ib < Kb; ++ib)")
         E("// primitive-pair data precomputed by the host shell-batcher: p, 1/p, P[3], PA[3], exp(-mu AB^2) da db")
-        E("const double* pp = A.ppair + (size_t)(it.ppoff + ia * Kb + ib) * 9;")
+        E("const double* pp = A.ppair + (size_t)(it.ppoff + ia * Kb + ib) * SI_PP_STRIDE;")
         E("const double p = pp[0], oop = pp[1];")
         E("const double P[3] = {pp[2], pp[3], pp[4]};")
         E("const double PA[3] = {pp[5], pp[6], pp[7]};")

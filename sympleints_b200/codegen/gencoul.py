@@ -193,7 +193,7 @@ class CoulGen:
         self.open("for (int ipp = 0; ipp < npp_max; ++ipp)")
         E("// pairs with fewer primitive pairs repeat their last one with zero weight")
         E("const int ippc = ipp < npp ? ipp : npp - 1;")
-        E("const double* pp = A.ppair + (size_t)(it.ppoff + ippc) * 9;")
+        E("const double* pp = A.ppair + (size_t)(it.ppoff + ippc) * SI_PP_STRIDE;")
         E("const double p = pp[0], oop = pp[1];")
         E("const double P0 = pp[2], P1 = pp[3], P2 = pp[4];")
         E("const double pref = ipp < npp ? 2.0 * SI_PI * oop * pp[8] : 0.0;")

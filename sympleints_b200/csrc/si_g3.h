@@ -26,6 +26,10 @@ struct BasisDev {
     const double* coef;
 };
 
+// doubles per primitive pair in the host-built pair table: p, 1/p, P[3], PA[3], exp(-mu AB^2) da db, exponent a,
+// exponent b, (pad) -- 96 bytes, so that one coalesced load brings everything a kernel needs about the pair
+#define SI_PP_STRIDE 12
+
 struct SiPairItem {   // 64 bytes: everything the kernels need about a shell pair in ONE load
     int sa, sb;       // shell indices; L(sa) >= L(sb)
     int swapped;      // packed layout: 1 if sa is the column shell of the (i>=j) block

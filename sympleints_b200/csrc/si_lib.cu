@@ -639,8 +639,9 @@ int si_init(int device, int lmax, int lauxmax, const double* boys_table, int nro
     SI_CUDA(cudaFuncSetAttribute(k_two_index, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     SI_CUDA(cudaFuncSetAttribute(k_coul, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     SI_CUDA(cudaFuncSetAttribute(k_3c2e, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    SI_CUDA(cudaFuncSetAttribute(k_onee<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    SI_CUDA(cudaFuncSetAttribute(k_onee<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    SI_CUDA(cudaFuncSetAttribute(k_onee<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    SI_CUDA(cudaFuncSetAttribute(k_onee<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    SI_CUDA(cudaFuncSetAttribute(k_onee<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     {
         // tables of the gto / prefactor kernels (per device)
         static SiGtoConst hg;
@@ -1020,7 +1021,7 @@ static int build_pair_set(si_basis* b, int i0, int i1, si_basis::PairSet* ps, bo
             }
         for (int variant = 0; variant < 2; ++variant) {
             const std::vector<double>& co = variant ? b->coef_pgto : b->coef;
-            std::vector<double> pp(npp * 9);
+            std::vector<double> pp(npp * SI_PP_STRIDE, 0.0);
             for (auto& kv : cls)
                 for (auto& it : kv.second) {
                     const int Ka = b->nprim[it.sa], Kb = b->nprim[it.sb];
@@ -1028,7 +1029,9 @@ static int build_pair_set(si_basis* b, int i0, int i1, si_basis::PairSet* ps, bo
                     const double* B = &b->cen[3 * it.sb];
                     for (int i = 0; i < Ka; ++i)
                         for (int j = 0; j < Kb; ++j) {
-                            double* q = &pp[((size_t)it.ppoff + (size_t)i * Kb + j) * 9];
+                            double* q = &pp[((size_t)it.ppoff + (size_t)i * Kb + j) * SI_PP_STRIDE];
+                            q[9] = b->exps[b->poff[it.sa] + i];
+                            q[10] = b->exps[b->poff[it.sb] + j];
                             const double ax = b->exps[b->poff[it.sa] + i], bx = b->exps[b->poff[it.sb] + j];
                             const double p = ax + bx, oop = 1.0 / p, mu = ax * bx * oop;
                             double r2 = 0.0;
@@ -1247,18 +1250,18 @@ static int run_onee(si_context* c, const si_basis* cb, unsigned mask, double* co
     std::sort(cls.begin(), cls.end(), [](const si_basis::PairClass* x, const si_basis::PairClass* y) {
         return si_ncart(x->La) * si_ncart(x->Lb) > si_ncart(y->La) * si_ncart(y->Lb);
     });
-    // two launches (classes with small / large blocks, see k_onee), concurrent on two streams
+    // three launches (classes by block size, see k_onee), concurrent on three streams
     Fan fan{c, user};
-    fan.limit = 2;
+    fan.limit = 3;
     rc = fan.begin();
     if (rc) return rc;
-    for (int big = 1; big >= 0; --big) {
+    for (int big = 2; big >= 0; --big) {
         OneEArgs A;
         memset(&A, 0, sizeof(A));
         int wsz_max = 0, g = 0, ns = 0;
         for (size_t i = 0; i < cls.size(); ++i) {
             const int la = cls[i]->La, lb = cls[i]->Lb, tpw = 32 / onee_ept(la, lb);
-            if ((int)onee_is_big(la, lb) != big) continue;
+            if (onee_size_class(la, lb) != big) continue;
             A.seg[ns].items = cls[i]->d_items;
             A.seg[ns].n = cls[i]->n;
             A.seg[ns].la = la;
@@ -1282,12 +1285,13 @@ static int run_onee(si_context* c, const si_basis* cb, unsigned mask, double* co
         const int warps = 4;
         const size_t smem = (size_t)warps * wsz_max * sizeof(double);
         // resident blocks per SM for this shared-memory size (cached per context: the occupancy query costs ~10 us of host time)
-        const size_t okey = smem * 2 + big;
+        const size_t okey = smem * 4 + big;
         auto occ_it = c->onee_occ.find(okey);
         if (occ_it == c->onee_occ.end()) {
             int occ = 0;
-            cudaError_t e = big ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_onee<4, true>, warps * 32, smem)
-                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_onee<4, false>, warps * 32, smem);
+            cudaError_t e = big == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_onee<4, 2>, warps * 32, smem)
+                            : big == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_onee<4, 1>, warps * 32, smem)
+                                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_onee<4, 0>, warps * 32, smem);
             if (e != cudaSuccess || occ < 1) occ = 1;
             occ_it = c->onee_occ.emplace(okey, occ).first;
         }
@@ -1295,10 +1299,12 @@ static int run_onee(si_context* c, const si_basis* cb, unsigned mask, double* co
         cudaStream_t s;
         rc = fan.stream(&s);
         if (rc) return rc;
-        if (big)
-            k_onee<4, true><<<grid, warps * 32, smem, s>>>(A, mask, wsz_max);
+        if (big == 2)
+            k_onee<4, 2><<<grid, warps * 32, smem, s>>>(A, mask, wsz_max);
+        else if (big == 1)
+            k_onee<4, 1><<<grid, warps * 32, smem, s>>>(A, mask, wsz_max);
         else
-            k_onee<4, false><<<grid, warps * 32, smem, s>>>(A, mask, wsz_max);
+            k_onee<4, 0><<<grid, warps * 32, smem, s>>>(A, mask, wsz_max);
         c->launches++;
         SI_CUDA(cudaGetLastError());
     }
@@ -2369,7 +2375,7 @@ int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int n
     size_t o = 0;
     auto take = [&](size_t nd) { size_t r = o; o += nd; return r; };
     const size_t o_int = take(8), o_ceno = take(6), o_exo = take(npo), o_coo = take(npo), o_cena = take(3), o_exa = take(npc),
-                 o_coa = take(npc), o_oexa = take(npc), o_pp = take((size_t)9 * npair), o_R = take(3), o_q = take(1),
+                 o_coa = take(npc), o_oexa = take(npc), o_pp = take((size_t)SI_PP_STRIDE * npair), o_R = take(3), o_q = take(1),
                  o_item = take(sizeof(SiPairItem) / 8), o_aitem = take(sizeof(SiAuxItem) / 8), o_cnt = take(1), o_out = take(n);
     std::vector<double> img(o, 0.0);
     int* hi = reinterpret_cast<int*>(&img[o_int]);   // L[2] nprim[2] poff[2] | aux: L nprim poff
@@ -2394,7 +2400,9 @@ int si_eval_block(si_context* c, int key, int La, int Lb, int Lc, int sph, int n
     }
     for (int i = 0; i < nps[0]; ++i)   // primitive-pair data of the single (a = shell 0, b = shell 1) item
         for (int j = 0; j < nps[1]; ++j) {
-            double* q = &img[o_pp + ((size_t)i * nps[1] + j) * 9];
+            double* q = &img[o_pp + ((size_t)i * nps[1] + j) * SI_PP_STRIDE];
+            q[9] = ex_[0][i];
+            q[10] = ex_[1][j];
             const double ax_ = ex_[0][i], bx_ = ex_[1][j];
             const double p_ = ax_ + bx_, oop = 1.0 / p_, mu = ax_ * bx_ * oop;
             double r2 = 0.0;

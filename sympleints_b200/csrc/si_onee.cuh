@@ -11,9 +11,9 @@
 //     T = Tx Sy Sz + Sx Ty Sz + Sx Sy Tz
 // lmn factors and C2S on both indices as main.py:122-189,250-272.
 //
-// Execution model: EPT lanes of a warp per shell pair.  Per primitive pair six lanes build the 1-D tables
-// (one lane per direction for the multipole tables e = 0..2, one per direction for the kinetic table) in
-// shared memory; then the lanes take Cartesian component pairs (a, b), form
+// Execution model: EPT lanes of a warp per shell pair.  Per primitive pair 6 (LB + 1) lanes build the 1-D tables
+// (lane = (multipole | kinetic, direction, ket index j), rows in registers, neighbours by warp shuffle) and publish
+// them in shared memory; then the lanes take Cartesian component pairs (a, b), form
 // the products for the requested operators and accumulate the contraction; per shell pair the two half
 // transforms C2S(a), C2S(b) run through shared memory and the block and its mirror image are stored.
 // The three-dimensional exp(-mu AB^2) da db (pi/p)^(3/2) is put into the x table; the y and z tables start at 1.
@@ -22,7 +22,7 @@
 
 #define ONEE_NCOMP 11   // 0 ovlp, 1 kin, 2-4 dpm x y z, 5-10 qpm xx xy xz yy yz zz
 #define ONEE_MAXL 4
-#define ONEE_KCH 12     // primitive pairs staged in shared memory at a time (12 doubles each)
+#define ONEE_KCH 12     // primitive pairs staged in shared memory at a time (SI_PP_STRIDE = 12 doubles each)
 
 #include "generated/onee_tables.inc"
 
@@ -68,86 +68,94 @@ __host__ __device__ constexpr int onee_wsz(int la, int lb) {
     return (w + 1) & ~1;
 }
 
-// one lane: all multipole tables I(i, j, e), e <= emax, of one direction, built in place in shared memory (the
-// lane reads back its own stores; no register arrays, so the kernel keeps a small register footprint)
+// Lane-parallel table build: lane (type, d, j) of a pair's lane group owns column j of direction d -- type 0 the
+// multipole tables I(i, j, e), e = 0..2, type 1 the overlap/kinetic pair S(i, j), T(i, j) -- and walks the rows
+// i = 0..LA with everything in registers; the only inter-lane dependence, the (i-1, j-1) neighbour of the bra
+// reduction (and (0, j-1), (0, j-2) in the first row), arrives by warp shuffle.  The dependent chain per primitive
+// pair is ~(LA + LB) steps of a shuffle and a few FMAs instead of (LA+1)(LB+1) x 3 entries read back through shared
+// memory by a single lane.  Needs 6 (LB + 1) <= EPT lanes per pair (30 for LB = 4).
 template <int LA, int LB>
-__device__ __forceinline__ void onee_multipole_tables(double* TB, int emax, double base, double PA, double PB, double PR,
-                                                      double oo2p) {
-    constexpr int TS = (LA + 1) * (LB + 1), JS = LB + 1;
-    for (int e = 0; e <= emax; ++e) {
-        double* I = TB + e * TS;
-        const double* Im = I - TS;   // order e - 1
-#pragma unroll
-        for (int j = 0; j <= LB; ++j)
-#pragma unroll
-            for (int i = 0; i <= LA; ++i) {
-                double v;
-                if (i > 0) {   // reduce the bra index
-                    double t = 0.0;
-                    if (i > 1) t = (double)(i - 1) * I[(i - 2) * JS + j];
-                    if (j > 0) t = fma((double)j, I[(i - 1) * JS + j - 1], t);
-                    if (e > 0) t = fma((double)e, Im[(i - 1) * JS + j], t);
-                    v = fma(oo2p, t, PA * I[(i - 1) * JS + j]);
-                } else if (j > 0) {   // i == 0: reduce the ket index
-                    double t = 0.0;
-                    if (j > 1) t = (double)(j - 1) * I[j - 2];
-                    if (e > 0) t = fma((double)e, Im[j - 1], t);
-                    v = fma(oo2p, t, PB * I[j - 1]);
-                } else if (e > 0) {   // i == j == 0: reduce the multipole index
-                    v = PR * Im[0];
-                    if (e > 1) v = fma(oo2p * (double)(e - 1), Im[-TS], v);
-                } else {
-                    v = base;
-                }
-                I[i * JS + j] = v;
-            }
+__device__ __forceinline__ void onee_tables_parallel(double* TB, const int q, const double* pp, const double* AB,
+                                                     const double* Rorg, const int origin_p, const bool live) {
+    constexpr int NJ = LB + 1, TS = (LA + 1) * NJ, DS = 5 * TS;
+    const int type = q / (3 * NJ), r = q - type * 3 * NJ, d = min(r / NJ, 2), j = r - (r / NJ) * NJ;
+    const bool act = q < 6 * NJ;
+    const double oop = pp[1], oo2p = 0.5 * oop;
+    const double PA = pp[5 + d], PB = PA + AB[d], PR = origin_p ? 0.0 : pp[2 + d] - Rorg[d];
+    const double a = pp[9], b = pp[10], bop = b * oop, aop = a * oop;
+    const double base = d == 0 ? (live ? pp[8] : 0.0) * (SI_PI * oop) * sqrt(SI_PI * oop) : 1.0;
+    const double fj = (double)j;
+    // channels: multipole lanes e = 0, 1, 2; kinetic lanes ch0 = S, ch1 = T
+    double c0, c1, c2;          // row i - 1 ... becomes row i
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0;   // row i - 2
+    // ---- row i = 0: column 0, then the ket recursion along j (lane j takes its turn at step jj == j)
+    if (type == 0) {
+        c0 = base;
+        c1 = PR * c0;
+        c2 = fma(oo2p, c0, PR * c1);
+    } else {
+        c0 = base;
+        c1 = (a - 2.0 * a * a * fma(PA, PA, oo2p)) * base;
+        c2 = 0.0;
     }
-}
-
-// one lane: kinetic table of one direction (needs the overlap table e = 0 of the same direction; the lane
-// rebuilds it in `S`, a scratch table of its own, so that it does not wait for the multipole lane)
-template <int LA, int LB>
-__device__ __forceinline__ void onee_kinetic_table(double* T, double* S, double base, double PA, double PB, double oo2p,
-                                                   double a, double b, double oop) {
-    constexpr int JS = LB + 1;
-    const double bop = b * oop, aop = a * oop;
 #pragma unroll
-    for (int j = 0; j <= LB; ++j)
-#pragma unroll
-        for (int i = 0; i <= LA; ++i) {
-            double s, t;
-            if (i > 0) {
-                double us = 0.0, ut = 0.0;
-                if (i > 1) {
-                    us = (double)(i - 1) * S[(i - 2) * JS + j];
-                    ut = (double)(i - 1) * T[(i - 2) * JS + j];
-                }
-                if (j > 0) {
-                    us = fma((double)j, S[(i - 1) * JS + j - 1], us);
-                    ut = fma((double)j, T[(i - 1) * JS + j - 1], ut);
-                }
-                s = fma(oo2p, us, PA * S[(i - 1) * JS + j]);
-                t = fma(oo2p, ut, PA * T[(i - 1) * JS + j]);
-                double w = 2.0 * a * s;
-                if (i > 1) w = fma(-(double)(i - 1), S[(i - 2) * JS + j], w);
-                t = fma(bop, w, t);
-            } else if (j > 0) {
-                s = PB * S[j - 1];
-                t = PB * T[j - 1];
-                if (j > 1) {
-                    s = fma(oo2p * (double)(j - 1), S[j - 2], s);
-                    t = fma(oo2p * (double)(j - 1), T[j - 2], t);
-                }
-                double w = 2.0 * b * s;
-                if (j > 1) w = fma(-(double)(j - 1), S[j - 2], w);
-                t = fma(aop, w, t);
-            } else {
-                s = base;
-                t = (a - 2.0 * a * a * fma(PA, PA, oo2p)) * s;
+    for (int jj = 1; jj <= LB; ++jj) {
+        const double m0 = __shfl_up_sync(0xffffffffu, c0, 1), m1 = __shfl_up_sync(0xffffffffu, c1, 1),
+                     m2 = __shfl_up_sync(0xffffffffu, c2, 1);
+        const double n0 = __shfl_up_sync(0xffffffffu, c0, 2), n1 = __shfl_up_sync(0xffffffffu, c1, 2),
+                     n2 = __shfl_up_sync(0xffffffffu, c2, 2);
+        if (j == jj) {
+            const double f = oo2p * (double)(jj - 1);
+            if (type == 0) {   // I(0, j, e) = PB I(0, j-1, e) + 1/(2p) [(j-1) I(0, j-2, e) + e I(0, j-1, e-1)]
+                c0 = fma(f, jj > 1 ? n0 : 0.0, PB * m0);
+                c1 = fma(oo2p, m0, fma(f, jj > 1 ? n1 : 0.0, PB * m1));
+                c2 = fma(2.0 * oo2p, m1, fma(f, jj > 1 ? n2 : 0.0, PB * m2));
+            } else {           // S(0, j), T(0, j)
+                const double sm2 = jj > 1 ? n0 : 0.0, tm2 = jj > 1 ? n1 : 0.0;
+                c0 = fma(f, sm2, PB * m0);
+                c1 = fma(aop, fma(-(double)(jj - 1), sm2, 2.0 * b * c0), fma(f, tm2, PB * m1));
             }
-            S[i * JS + j] = s;
-            T[i * JS + j] = t;
         }
+    }
+    double* dstM = TB + d * DS + j;            // multipole: + e * TS + i * NJ
+    double* dstT = TB + d * DS + 3 * TS + j;   // kinetic T: + i * NJ
+    if (act) {
+        if (type == 0) {
+            dstM[0] = c0;
+            dstM[TS] = c1;
+            dstM[2 * TS] = c2;
+        } else {
+            dstT[0] = c1;
+        }
+    }
+    // ---- rows i = 1..LA: bra reduction; the (i-1, j-1) neighbour comes from the lane below
+#pragma unroll
+    for (int i = 1; i <= LA; ++i) {
+        const double m0 = __shfl_up_sync(0xffffffffu, c0, 1), m1 = __shfl_up_sync(0xffffffffu, c1, 1),
+                     m2 = __shfl_up_sync(0xffffffffu, c2, 1);
+        const double fi = (double)(i - 1);
+        double n0, n1, n2;
+        if (type == 0) {   // I(i,j,e) = PA I(i-1,j,e) + 1/(2p) [(i-1) I(i-2,j,e) + j I(i-1,j-1,e) + e I(i-1,j,e-1)]
+            n0 = fma(oo2p, fma(fi, p0, fj * m0), PA * c0);
+            n1 = fma(oo2p, fma(fi, p1, fma(fj, m1, c0)), PA * c1);
+            n2 = fma(oo2p, fma(fi, p2, fma(fj, m2, 2.0 * c1)), PA * c2);
+        } else {           // S(i,j), T(i,j) = PA T(i-1,j) + 1/(2p)[..] + (b/p) [2a S(i,j) - (i-1) S(i-2,j)]
+            n0 = fma(oo2p, fma(fi, p0, fj * m0), PA * c0);
+            n1 = fma(bop, fma(-fi, p0, 2.0 * a * n0), fma(oo2p, fma(fi, p1, fj * m1), PA * c1));
+            n2 = 0.0;
+        }
+        p0 = c0; p1 = c1; p2 = c2;
+        c0 = n0; c1 = n1; c2 = n2;
+        if (act) {
+            if (type == 0) {
+                dstM[i * NJ] = c0;
+                dstM[TS + i * NJ] = c1;
+                dstM[2 * TS + i * NJ] = c2;
+            } else {
+                dstT[i * NJ] = c1;
+            }
+        }
+    }
 }
 
 template <int LA, int LB>
@@ -184,39 +192,19 @@ __device__ void onee_body(const OneEArgs& A, const OneEClassSeg& sg, int grp_in_
     for (int o = 16; o >= EPT; o >>= 1) Kmax = max(Kmax, __shfl_xor_sync(0xffffffffu, Kmax, o));
     const int emax = (mask & 0x7E0u) ? 2 : ((mask & 0x1Cu) ? 1 : 0);
     const bool want_kin = (mask & 2u) != 0;
-    const int pa0 = A.poff[it.sa], pb0 = A.poff[it.sb];
     // Stage the data of primitive pairs [k0, k0 + ONEE_KCH) with coalesced loads: one global round trip per chunk
     // instead of one (dependent) per primitive pair.
     auto stage = [&](int k0) {
         const int nk = max(0, min(ONEE_KCH, K - k0));   // (0 for pairs with fewer primitives: they keep their last chunk)
-        for (int i = q; i < nk * 12; i += EPT) {
-            const int k = i / 12, j = i - k * 12;
-            double v = 0.0;
-            if (j < 9) {
-                v = A.ppair[(size_t)(it.ppoff + k0 + k) * 9 + j];
-            } else if (j == 9) {
-                v = A.exps[pa0 + (k0 + k) / it.Kb];
-            } else if (j == 10) {
-                v = A.exps[pb0 + (k0 + k) % it.Kb];
-            }
-            PP[i] = v;
-        }
+        const double* src = A.ppair + (size_t)(it.ppoff + k0) * SI_PP_STRIDE;   // (the exponents a, b ride along)
+        for (int i = q; i < nk * SI_PP_STRIDE; i += EPT) PP[i] = src[i];
         __syncwarp();
     };
     auto build_tables = [&](int kk, bool live, int e_hi, bool kin) {
-        const double* pp = PP + kk * 12;
-        if (q < 6) {
-            const int d = q % 3;
-            const double oop = pp[1];
-            const double PA = pp[5 + d], PB = PA + it.AB[d], oo2p = 0.5 * oop;
-            // (pi/p)^(3/2) exp(-mu AB^2) da db in the x table, 1 in y and z; pairs with fewer primitives add zeros
-            const double base = d == 0 ? (live ? pp[8] : 0.0) * (SI_PI * oop) * sqrt(SI_PI * oop) : 1.0;
-            if (q < 3) {
-                onee_multipole_tables<LA, LB>(TB + d * DS, e_hi, base, PA, PB, A.origin_p ? 0.0 : pp[2 + d] - A.R[d], oo2p);
-            } else if (kin) {
-                onee_kinetic_table<LA, LB>(TB + d * DS + 3 * TS, TB + d * DS + 4 * TS, base, PA, PB, oo2p, pp[9], pp[10], oop);
-            }
-        }
+        // (pi/p)^(3/2) exp(-mu AB^2) da db goes into the x tables, 1 into y and z; pairs with fewer primitives add zeros
+        (void)e_hi;
+        (void)kin;
+        onee_tables_parallel<LA, LB>(TB, q, PP + kk * 12, it.AB, A.R, A.origin_p, live);
         __syncwarp();
     };
     // with one primitive pair the tables are built once and shared by all passes
@@ -334,15 +322,20 @@ __device__ void onee_body(const OneEArgs& A, const OneEClassSeg& sg, int grp_in_
     if constexpr (3 * CP < ONEE_NCOMP) run_pass(std::integral_constant<int, 3 * CP>{});
 }
 
-// Two instantiations: BIG = false holds the classes with at most 60 Cartesian component pairs (small shared-memory
-// and register footprint -> many resident warps, which is what hides the long dependent chains of these groups),
-// BIG = true the rest ((ff), (gd), (gf), (gg)).  The two launches of a call run concurrently on two streams.
-__host__ __device__ constexpr bool onee_is_big(int la, int lb) {
-    return ((la + 1) * (la + 2) / 2) * ((lb + 1) * (lb + 2) / 2) > 60;
+// Three instantiations by block size (Cartesian component pairs NAB): SIZE 0 = NAB <= 18 ((ss) ... (dp), (fs), (gs): most
+// of the shell pairs; small shared-memory and register footprint -> many resident warps, which is what hides the
+// dependent global-load chains of these short groups), SIZE 1 = NAB <= 60, SIZE 2 the rest ((ff), (gd), (gf), (gg)).
+// The launches of a call run concurrently on the context's streams.
+__host__ __device__ constexpr int onee_size_class(int la, int lb) {
+    const int nab = ((la + 1) * (la + 2) / 2) * ((lb + 1) * (lb + 2) / 2);
+    return nab <= 18 ? 0 : (nab <= 60 ? 1 : 2);
 }
+#ifndef ONEE_MB0
+#define ONEE_MB0 6
+#endif
 
-template <int WARPS, bool BIG>
-__global__ void __launch_bounds__(WARPS * 32, BIG ? 3 : 4) k_onee(OneEArgs A, unsigned mask, int wsz_max) {
+template <int WARPS, int SIZE>
+__global__ void __launch_bounds__(WARPS * 32, SIZE == 0 ? ONEE_MB0 : (SIZE == 1 ? 4 : 3)) k_onee(OneEArgs A, unsigned mask, int wsz_max) {
     extern __shared__ double onee_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* wbase = onee_smem + (size_t)warp * wsz_max;
@@ -363,7 +356,7 @@ __global__ void __launch_bounds__(WARPS * 32, BIG ? 3 : 4) k_onee(OneEArgs A, un
         switch (sg.la * 5 + sg.lb) {
 #define ONEE_CASE(LA, LB)                                                                      \
     case LA * 5 + LB:                                                                          \
-        if constexpr (onee_is_big(LA, LB) == BIG) onee_body<LA, LB>(A, sg, gi, lane, wbase, mask); \
+        if constexpr (onee_size_class(LA, LB) == SIZE) onee_body<LA, LB>(A, sg, gi, lane, wbase, mask); \
         break;
             ONEE_CASE(0, 0) ONEE_CASE(1, 0) ONEE_CASE(1, 1) ONEE_CASE(2, 0) ONEE_CASE(2, 1) ONEE_CASE(2, 2)
             ONEE_CASE(3, 0) ONEE_CASE(3, 1) ONEE_CASE(3, 2) ONEE_CASE(3, 3)

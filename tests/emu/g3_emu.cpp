@@ -60,12 +60,12 @@ extern "C" int g3emu_eval(int La, int Lb, int Lc, int Ka, const double* ax, cons
     SiPairItem& item = items[0];
     item.sa = 0;
     item.sb = 1;
-    std::vector<double> pp((size_t)npairs * Ka * Kb * 9);
+    std::vector<double> pp((size_t)npairs * Ka * Kb * SI_PP_STRIDE, 0.0);
     for (int ipair = 0; ipair < npairs; ++ipair)
     for (int i = 0; i < Ka; ++i)
         for (int j = 0; j < Kb; ++j) {
             const double* A = ipair ? A2 : A_;
-            double* q = &pp[((size_t)ipair * Ka * Kb + (size_t)(i * Kb + j)) * 9];
+            double* q = &pp[((size_t)ipair * Ka * Kb + (size_t)(i * Kb + j)) * SI_PP_STRIDE];
             double p = ax[i] + bx[j], oop = 1.0 / p, mu = ax[i] * bx[j] * oop, r2 = 0.0;
             q[0] = p;
             q[1] = oop;

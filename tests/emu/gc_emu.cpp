@@ -40,13 +40,13 @@ extern "C" int gcemu_eval(int La, int Lb, int npairs, const int* Ka, const doubl
         it.Kb = Kb[ip];
         it.fa0 = ip * (na + nb);
         it.fb0 = it.fa0 + na;
-        it.ppoff = (int)(pp.size() / 9);
+        it.ppoff = (int)(pp.size() / SI_PP_STRIDE);
         const double* Ai = A + 3 * ip;
         const double* Bi = B + 3 * ip;
         for (int d = 0; d < 3; ++d) it.AB[d] = Ai[d] - Bi[d];
         for (int i = 0; i < Ka[ip]; ++i)
             for (int j = 0; j < Kb[ip]; ++j) {
-                double q[9];
+                double q[SI_PP_STRIDE] = {0};
                 const double a = ax[oa + i], b = bx[ob + j];
                 const double p = a + b, oop = 1.0 / p, mu = a * b * oop;
                 double r2 = 0.0;
@@ -58,7 +58,7 @@ extern "C" int gcemu_eval(int La, int Lb, int npairs, const int* Ka, const doubl
                     r2 += (Ai[d] - Bi[d]) * (Ai[d] - Bi[d]);
                 }
                 q[8] = exp(-mu * r2) * da[oa + i] * db[ob + j];
-                pp.insert(pp.end(), q, q + 9);
+                pp.insert(pp.end(), q, q + SI_PP_STRIDE);
             }
         oa += Ka[ip];
         ob += Kb[ip];

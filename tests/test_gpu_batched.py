@@ -52,14 +52,14 @@ def test_one_electron_matrices(engine, small, key, sph):
 
 @pytest.mark.parametrize("normalize", ["cgto", "pgto"])
 def test_one_electron_set_in_one_launch(engine, small, normalize):
-    """si_int1e_set: ovlp, kin, dpm, qpm of all classes from the fused kernel k_onee (two concurrent launches: the
-    classes with small and with large blocks), against the oracle and bit-identical to the per-key calls (same
+    """si_int1e_set: ovlp, kin, dpm, qpm of all classes from the fused kernel k_onee (three concurrent launches: the
+    classes by block size), against the oracle and bit-identical to the per-key calls (same
     kernel, operator mask)."""
     shells, _, _, ob, _ = small
     R = np.array([0.3, -0.2, 0.5])
     l0 = engine.launch_count()
     S = engine.int1e_set(ob, normalize=normalize, R=R)
-    assert engine.launch_count() - l0 <= 2
+    assert engine.launch_count() - l0 <= 3
     S = S.cpu().numpy()
     for key, o0, n in (("ovlp", 0, 1), ("kin", 1, 1), ("dpm", 2, 3), ("qpm", 5, 6)):
         o = oracle_matrix(key, shells, normalize=normalize, R=R)
