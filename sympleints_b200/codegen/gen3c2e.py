@@ -38,6 +38,25 @@ if _os.environ.get("SI_G3_EPT_SHIFT"):
 
 
 
+# cache of the layout / HRR-item-order search (ClassGen._layout): deterministic, but a few seconds per class
+_HRR_FILE = _os.path.join(_os.path.dirname(__file__), "hrr_orders.json")
+_HRR_CACHE = {}
+if _os.path.exists(_HRR_FILE) and not _os.environ.get("SI_G3_NO_HRR_CACHE"):
+    try:
+        _HRR_CACHE = _json.load(open(_HRR_FILE))
+    except Exception:
+        _HRR_CACHE = {}
+
+
+def _save_hrr_cache():
+    try:
+        tmp = _HRR_FILE + ".tmp%d" % _os.getpid()
+        _json.dump(_HRR_CACHE, open(tmp, "w"), sort_keys=True)
+        _os.replace(tmp, _HRR_FILE)
+    except Exception:
+        pass
+
+
 # ----------------------------------------------------------------------------------------
 # small helpers (orderings identical to sympleints/helpers.py:42-49)
 # ----------------------------------------------------------------------------------------
@@ -203,14 +222,28 @@ class ClassGen:
         strided accesses of the contracted phase (lanes differ in (component, m)) spread over the
         banks; the paddings are found by simulating the half-warp bank pattern (_conflicts)."""
         if ypad is None:
+            # the search result is cached (per class and lanes-per-tuple) in codegen/hrr_orders.json
+            key = f"{self.La}{self.Lb}{self.Lc}_e{self.EPT}_y{int(self.YREG)}"
+            hit = _HRR_CACHE.get(key)
+            if hit is not None:
+                self._layout(hit["yp"], hit["zp"])
+                self.hrr_order = [tuple(x) for x in hit["order"]] if hit["order"] is not None else None
+                self.hrr_cost, self.hrr_cost_natural, self.hrr_cost_ideal = hit.get("cost"), hit.get("natural"), hit.get("ideal")
+                return
             best = None
             for yp in range(0, 8):
-                for zp in [0]:
+                for zp in (range(0, 4) if self.Lb > 0 else [0]):
                     self._layout(yp, zp)
-                    c = (self._conflicts(), self.WSZ)
+                    self.hrr_order = None
+                    order, c = self._order_hrr_items(descent=False)   # constructive orders only: cheap
+                    c = (c + self._conflicts_c2sa(), self.WSZ)
                     if best is None or c < best[0]:
-                        best = (c, yp, zp)
+                        best = (c, yp, zp, order)
             self._layout(best[1], best[2])
+            self.hrr_order, self.hrr_cost = self._order_hrr_items(descent=True)
+            _HRR_CACHE[key] = {"yp": best[1], "zp": best[2], "order": self.hrr_order, "cost": self.hrr_cost,
+                               "natural": getattr(self, "hrr_cost_natural", None), "ideal": getattr(self, "hrr_cost_ideal", None)}
+            _save_hrr_cache()
             return
         L, Lc = self.L, self.Lc
         o = 0
@@ -229,6 +262,7 @@ class ClassGen:
         # Z (after HRR + C2S(b)) is laid out [a][jb][m], m fastest: the C2S(a) stage then reads consecutive
         # words per lane (its items are (jb, m), m fastest, which also keeps the global stores coalesced)
         self.ZS = self.YS if self.Lb == 0 else None
+        self.ZA = None
         self.Y_OFF = o
         o += self.nm * self.YS
         prim_start = o
@@ -250,7 +284,10 @@ class ClassGen:
             z_end = prim_start
         else:
             self.Z_OFF = prim_start
-            z_end = prim_start + self.nca * self.nsb * self.nm
+            # Z[a][jb][m]: the stride between target components a is padded so that the stores of one HRR round
+            # (lanes = (a, m) items, one store per jb) spread over the banks
+            self.ZA = self.nsb * self.nm + zpad
+            z_end = prim_start + self.nca * self.ZA
         w = max(prim_end, z_end)
         # Several tuples share a warp when EPT < 32; a half-warp (one shared-memory wavefront of 8-byte
         # accesses, 16 banks) then holds 16/EPT tuples whose lanes touch ~EPT consecutive words each, so the
@@ -260,59 +297,134 @@ class ClassGen:
             w += 1
         self.WSZ = w
 
-    def _conflicts(self):
-        """Shared-memory wavefronts of the strided stages (HRR gather, Z store, C2S(a) loads) for the
-        current layout: per LDS.64/STS.64 each half-warp costs as many wavefronts as the largest number
-        of distinct addresses that fall into one 8-byte bank (16 banks)."""
-        EPT, TPW = self.EPT, self.TPW
-        nm, nca, nsb, La, Lb = self.nm, self.nca, self.nsb, self.La, self.Lb
+    def _half_warp_cost(self, addrs):
+        """Shared-memory wavefronts of one 8-byte access of a half-warp: the largest number of DISTINCT addresses
+        that fall into one of the 16 banks (equal addresses are a broadcast)."""
+        banks = {}
+        for a in addrs:
+            if a is not None:
+                banks.setdefault(a % 16, set()).add(a)
+        return max((len(v) for v in banks.values()), default=0)
 
-        def cost(addrs):
-            tot = 0
-            for h in (addrs[:16], addrs[16:]):
-                banks = {}
-                for a in h:
-                    if a is None:
-                        continue
-                    banks.setdefault(a % 16, set()).add(a)
-                tot += max((len(v) for v in banks.values()), default=0)
-            return tot
+    def _hrr_loads(self):
+        ks = [k for n in range(self.Lb + 1) for k in cart_order(n)]
+        out = []
+        for k in ks:
+            ik = k[1] + k[2]
+            out.append((ik, off(self.La + sum(k)) - off(self.La) + ik * (ik + 1) // 2 + k[2]))
+        return out
 
+    def _order_hrr_items(self, descent=True):
+        """Order of the HRR work items (target component ai, spherical aux component m) over the lanes.
+
+        Every item gathers T(Lb) inputs Y[m][a + k]; with the items in natural order (a fastest) the lanes of a
+        half-warp span several rows of the component triangle and nearly every gather with k_y + k_z > 0 is 2-way
+        bank-conflicted (measured: 46 % excess wavefronts in the gather, the largest single consumer of the
+        shared-memory pipe for Lb >= 2).  Items of the SAME triangle row differ by a k-independent address offset,
+        so a half-warp filled from one row (and m values whose row offsets tile the banks) is conflict-free for all
+        k at once.  Found here by a greedy construction + pairwise-swap descent on the exact wavefront model
+        (gather loads + Z stores), per class, at generation time."""
+        if self.Lb == 0:
+            return None, 0
+        import random
+        EPT, nm, nca, WSZ = self.EPT, self.nm, self.nca, self.WSZ
+        loads = self._hrr_loads()
+        row = {}
+        for ai in range(nca):
+            r = 0
+            while (r + 1) * (r + 2) // 2 <= ai:
+                r += 1
+            row[ai] = r
+        items = [(m, ai) for m in range(nm) for ai in range(nca)]
+        nit = len(items)
+        nround = (nit + EPT - 1) // EPT
+        lanes_per_half = min(EPT, 16)
+        tuples_per_half = 16 // lanes_per_half
+
+        import numpy as np
+        nld = len(loads)
+        # address of every access of an item: T(Lb) gathers, then nsb stores (distinct items never share an address)
+        A = np.empty((nit, nld + self.nsb), dtype=np.int64)
+        for idx, (m, ai) in enumerate(items):
+            for j, ld in enumerate(loads):
+                A[idx, j] = self.Y_OFF + m * self.YS + ai + row[ai] * ld[0] + ld[1]
+            for jb in range(self.nsb):
+                A[idx, nld + jb] = self.Z_OFF + ai * self.ZA + jb * nm + m
+        toff = (np.arange(tuples_per_half, dtype=np.int64) * WSZ)[:, None, None]
+        eye = np.arange(16, dtype=np.int64)
+
+        def half_cost(idxs):
+            """Wavefronts of all accesses of one half-warp holding the items `idxs` (of each of its tuples)."""
+            banks = ((A[idxs][None, :, :] + toff) % 16).reshape(-1, A.shape[1])        # (lanes, accesses)
+            cnt = (banks[:, :, None] == eye).sum(axis=0)                                    # (accesses, 16)
+            return int(cnt.max(axis=1).sum())
+
+        def round_cost(chunk):
+            return sum(half_cost(chunk[h0:h0 + lanes_per_half]) for h0 in range(0, len(chunk), lanes_per_half))
+
+        def total(order):
+            return sum(round_cost(order[r * EPT:(r + 1) * EPT]) for r in range(nround))
+
+        pos = {it: i for i, it in enumerate(items)}
+        natural = list(range(nit))                                  # a fastest (round-1 order)
+        mfast = [pos[(m, ai)] for ai in range(nca) for m in range(nm)]
+        rowm = sorted(range(nit), key=lambda i: (-row[items[i][1]], items[i][0], items[i][1]))
+        rowa = sorted(range(nit), key=lambda i: (-row[items[i][1]], items[i][1], items[i][0]))
+        cands = [natural, mfast, rowm, rowa]
+        best = min(cands, key=total)
+        bc = total(best)
+        self.hrr_cost_natural = total(natural)
+        nhalf = sum((min(nit - r * EPT, EPT) + lanes_per_half - 1) // lanes_per_half for r in range(nround))
+        self.hrr_cost_ideal = nhalf * A.shape[1]
+        if not descent or bc <= self.hrr_cost_ideal:
+            return [items[i] for i in best], bc
+        # simulated annealing over pairwise swaps between different half-warps (deterministic seed per class)
+        rng = random.Random(1234 + 100 * self.La + 10 * self.Lb + self.Lc)
+        order = list(best)
+        nh = (nit + lanes_per_half - 1) // lanes_per_half
+        hc = [half_cost(order[h * lanes_per_half:(h + 1) * lanes_per_half]) for h in range(nh)]
+        cur = sum(hc)
+        best_order, best_cost = list(order), cur
+        iters = int(_os.environ.get("SI_G3_HRR_ITERS", "12000"))
+        for t in range(iters):
+            if best_cost <= self.hrr_cost_ideal:
+                break
+            temp = 1.5 * (1.0 - t / iters) + 0.05
+            i, j = rng.randrange(nit), rng.randrange(nit)
+            hi, hj = i // lanes_per_half, j // lanes_per_half
+            if hi == hj:
+                continue
+            order[i], order[j] = order[j], order[i]
+            ci = half_cost(order[hi * lanes_per_half:(hi + 1) * lanes_per_half])
+            cj = half_cost(order[hj * lanes_per_half:(hj + 1) * lanes_per_half])
+            delta = ci + cj - hc[hi] - hc[hj]
+            if delta <= 0 or rng.random() < math.exp(-delta / temp):
+                hc[hi], hc[hj] = ci, cj
+                cur += delta
+                if cur < best_cost:
+                    best_order, best_cost = list(order), cur
+            else:
+                order[i], order[j] = order[j], order[i]
+        return [items[i] for i in best_order], best_cost
+
+    def _conflicts_c2sa(self):
+        """Wavefronts of the C2S(a) loads for the current layout (see _half_warp_cost)."""
+        EPT, nm, nca, nsb = self.EPT, self.nm, self.nca, self.nsb
+        lanes_per_half = min(EPT, 16)
+        tuples_per_half = 16 // lanes_per_half
         total = 0
-        if Lb > 0:
-            nit = nca * nm
-            ks = [k for n in range(Lb + 1) for k in cart_order(n)]
-            for r in range((nit + EPT - 1) // EPT):
-                lanes = []
-                for lane in range(32):
-                    q, tl = lane % EPT, lane // EPT
-                    item = q + EPT * r
-                    if item >= nit:
-                        lanes.append(None)
-                        continue
-                    m, ai = divmod(item, nca)
-                    ia = 0
-                    while (ia + 1) * (ia + 2) // 2 <= ai:
-                        ia += 1
-                    lanes.append((tl, ai, m, ia))
-                for k in ks:
-                    ik = k[1] + k[2]
-                    const = off(La + sum(k)) - off(La) + ik * (ik + 1) // 2 + k[2]
-                    total += cost([None if t is None else t[0] * self.WSZ + self.Y_OFF + t[2] * self.YS + t[1] + t[3] * ik + const
-                                   for t in lanes])
-                for jb in range(nsb):
-                    total += cost([None if t is None else t[0] * self.WSZ + self.Z_OFF + (t[1] * nsb + jb) * nm + t[2]
-                                   for t in lanes])
-        else:
-            nit = nsb * nm
-            for r in range((nit + EPT - 1) // EPT):
-                lanes = []
-                for lane in range(32):
-                    q, tl = lane % EPT, lane // EPT
-                    item = q + EPT * r
-                    lanes.append(None if item >= nit else (tl,) + divmod(item, nm))
+        nit = nsb * nm
+        for r in range((nit + EPT - 1) // EPT):
+            chunk = [q + EPT * r for q in range(EPT) if q + EPT * r < nit]
+            for h0 in range(0, len(chunk), lanes_per_half):
+                part = chunk[h0:h0 + lanes_per_half]
                 for a in range(nca):
-                    total += cost([None if t is None else t[0] * self.WSZ + self.Z_OFF + t[2] * self.ZS + a * nsb + t[1] for t in lanes])
+                    if self.Lb > 0:
+                        ad = [self.Z_OFF + a * self.ZA + item + t * self.WSZ for t in range(tuples_per_half) for item in part]
+                    else:
+                        ad = [self.Z_OFF + (item % nm) * self.ZS + a * nsb + item // nm + t * self.WSZ
+                              for t in range(tuples_per_half) for item in part]
+                    total += self._half_warp_cost(ad)
         return total
 
     # ---- emission helpers ---------------------------------------------------------------
@@ -432,6 +544,14 @@ class ClassGen:
                     v |= (ent[d][1] & 0xF) << (4 * d)
                 vals.append(v)
             E(f"__device__ const int g3_df_{name}[{len(vals)}] = {{{', '.join(map(str, vals))}}};")
+        if Lb > 0:
+            vals = []
+            for (m, ai) in self.hrr_order:
+                r = 0
+                while (r + 1) * (r + 2) // 2 <= ai:
+                    r += 1
+                vals.append((self.Y_OFF + m * self.YS + ai) | (r << 13) | ((self.Z_OFF + ai * self.ZA + m) << 16))
+            E(f"__device__ const int g3_hm_{name}[{len(vals)}] = {{{', '.join(map(str, vals))}}};")
         E("")
         E(f"// class ({La}{Lb}|{Lc}): EPT={EPT} lanes per tuple, {TPW} tuples per warp, {self.WSZ} doubles of shared memory per tuple")
         E("// TAB: the group's tuples come from the host-built table A.tuples.  A template parameter, not a run-time")
@@ -461,10 +581,10 @@ class ClassGen:
         E("")
         if Lb > 0:
             nit_h = self.nca * self.nm
-            E("// HRR work items (target a component, m), a fastest: Y base address | row of a << 13 | Z address << 16")
+            E("// HRR work items (target a component, m) in the bank-conflict-free order found by the generator:")
+            E("// Y base address | row of a << 13 | Z address << 16")
             self.open(f"for (int item = q; item < {nit_h}; item += EPT)")
-            E(f"const int m = item / {self.nca}, ai = item - m * {self.nca};")
-            E(f"((int*)&W[{self.HM_OFF}])[item] = ({self.Y_OFF} + m * {self.YS} + ai) | (si_g3_tri_row(ai) << 13) | (({self.Z_OFF} + ai * {self.nsb * self.nm} + m) << 16);")
+            E(f"((int*)&W[{self.HM_OFF}])[item] = g3_hm_{name}[item];")
             self.close()
             self.sync()
         # ---- work loop over tuple groups
@@ -826,7 +946,7 @@ class ClassGen:
         E(f"const int jb = item / {nm}, m = item - jb * {nm};")
         for a in range(nca):
             if self.Lb > 0:
-                E(f"const double z{a} = W[{self.Z_OFF + a * nsb * nm} + item];")
+                E(f"const double z{a} = W[{self.Z_OFF + a * self.ZA} + item];")
             else:
                 E(f"const double z{a} = W[{self.Z_OFF} + m * {self.ZS} + {a * nsb} + jb];")
         for ia in range(nsa):
