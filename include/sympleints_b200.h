@@ -163,6 +163,14 @@ int si_int3c2e_h(si_context* ctx, const si_basis* orb, const si_basis* aux, int 
                  int aux_shell_end, int normalize, int layout, double* out_host, size_t out_len);
 
 /*
+ * Schwarz integrals (section 8f-2; sympleints/graphs/defs/int_4c2e.py, l_iters.py:23-28 `schwarz_iter`): D_dev (nbf, nbf)
+ * receives D[mu, nu] = (mu nu|mu nu) for the spherical functions of the set, Q_dev (nshell, nshell; may be NULL) the
+ * shell-pair factors Q[a, b] = sqrt(max_{mu in a, nu in b} D[mu, nu]), so that |(ab|P)| <= Q[a, b] sqrt((P|P)).
+ * Needs Boys orders up to 4 lmax (SI_ERR_BOYS if the caller's table is smaller).
+ */
+int si_schwarz(si_context* ctx, const si_basis* basis, int normalize, double* D_dev, double* Q_dev, void* stream);
+
+/*
  * Opt-in primitive pre-screening of the 3c2e kernels (eps = 0 switches it off; that is the default, the parity mode and
  * the benchmark mode -- the reference's own estimate, graphs/templates/int_3c2e_func.tpl:46-54, is a no-op `continue`).
  * A primitive triple is skipped when prefactor^2 * min(1, pi / (4 T)) <= eps^2 for all tuples of a warp, i.e. when the

@@ -16,7 +16,8 @@ LIB = LIBDIR / "libsympleints_b200.so"
 GENDIR = CSRC / "generated"
 OBJDIR = PKG / "lib" / "obj"
 SOURCES = [CSRC / "si_lib.cu", CSRC / "si_program.cpp"]
-HEADERS = [CSRC / "si_machine.h", CSRC / "si_program.h", CSRC / "si_onee.cuh", PKG.parent / "include" / "sympleints_b200.h"]
+HEADERS = [CSRC / "si_machine.h", CSRC / "si_program.h", PKG.parent / "include" / "sympleints_b200.h"]
+LIB_HEADERS = [CSRC / "si_onee.cuh", CSRC / "si_gto.cuh", CSRC / "si_schwarz.cuh"]   # included by si_lib.cu only
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -58,7 +59,7 @@ def _compile_obj(src, obj, verbose):
 
 def build_library(force=False, verbose=False, jobs=None):
     gen = generate_sources()
-    deps = SOURCES + HEADERS + [CSRC / "si_g3.h", PKG / "codegen" / "gen3c2e.py", PKG / "codegen" / "gencoul.py", PKG / "codegen" / "genonee.py",
+    deps = SOURCES + HEADERS + LIB_HEADERS + [CSRC / "si_g3.h", PKG / "codegen" / "gen3c2e.py", PKG / "codegen" / "gencoul.py", PKG / "codegen" / "genonee.py",
                                 GENDIR / "g3_table.inc", GENDIR / "gc_table.inc"] + gen
     for tj in (PKG / "codegen" / "tuning.json", PKG / "codegen" / "tuning_coul.json"):
         if tj.exists():
@@ -77,8 +78,10 @@ def build_library(force=False, verbose=False, jobs=None):
         obj = OBJDIR / (src.stem + ".o")
         objs.append(obj)
         if force or not obj.exists() or obj.stat().st_mtime < max(src.stat().st_mtime, hdr_time) or \
-                (src.name == "si_lib.cu" and obj.stat().st_mtime < max((GENDIR / "g3_table.inc").stat().st_mtime,
-                                                                        (GENDIR / "gc_table.inc").stat().st_mtime)):
+                (src.name == "si_lib.cu" and obj.stat().st_mtime < max([(GENDIR / "g3_table.inc").stat().st_mtime,
+                                                                         (GENDIR / "gc_table.inc").stat().st_mtime,
+                                                                         (GENDIR / "onee_tables.inc").stat().st_mtime] +
+                                                                        [h.stat().st_mtime for h in LIB_HEADERS])):
             todo.append((src, obj))
     jobs = jobs or max(1, min(8, (os.cpu_count() or 2)))
     with cf.ThreadPoolExecutor(jobs) as ex:

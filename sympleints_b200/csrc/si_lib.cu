@@ -33,6 +33,7 @@
 #include "generated/gc_table.inc"
 #include "si_onee.cuh"
 #include "si_gto.cuh"
+#include "si_schwarz.cuh"
 
 // ---------------------------------------------------------------------------
 // device-side data
@@ -597,7 +598,7 @@ int si_init(int device, int lmax, int lauxmax, const double* boys_table, int nro
         c->nrows = nrows;
         c->ncols = ncols;
     } else {
-        int need = std::max(2 * lmax + lauxmax, 2 * lauxmax);  // highest Boys order
+        int need = std::max(std::max(2 * lmax + lauxmax, 2 * lauxmax), 4 * lmax);  // highest Boys order (4 lmax: Schwarz integrals)
         build_boys_table(std::max(need, 8), c->boys_host, c->nrows, c->ncols);
     }
     const int nmax = c->nrows - 7;
@@ -639,6 +640,7 @@ int si_init(int device, int lmax, int lauxmax, const double* boys_table, int nro
     SI_CUDA(cudaFuncSetAttribute(k_two_index, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     SI_CUDA(cudaFuncSetAttribute(k_coul, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     SI_CUDA(cudaFuncSetAttribute(k_3c2e, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    SI_CUDA(cudaFuncSetAttribute(k_schwarz, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     SI_CUDA(cudaFuncSetAttribute(k_onee<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     SI_CUDA(cudaFuncSetAttribute(k_onee<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     SI_CUDA(cudaFuncSetAttribute(k_onee<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
@@ -1944,6 +1946,52 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
     }
     rc = fan.end();
     return rc;
+}
+
+// ---- Schwarz integrals (ab|ab) ---------------------------------------------------
+int si_schwarz(si_context* c, const si_basis* cb, int normalize, double* D_dev, double* Q_dev, void* stream) {
+    if (!c || !cb || !D_dev) return SI_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    si_basis* b = const_cast<si_basis*>(cb);
+    if (b->lmax > c->lmax || b->lmax > SI_GTO_LMAX) return SI_ERR_LMAX;
+    if (4 * b->lmax > c->nrows - 7) {
+        g_last_error = "Boys table too small for the Schwarz integrals of this basis (orders up to 4 lmax)";
+        return SI_ERR_BOYS;
+    }
+    SI_CUDA(cudaSetDevice(c->device));
+    int rc = build_pair_classes(b);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c->ev_last_valid) SI_CUDA(cudaStreamWaitEvent(s, c->ev_last, 0));
+    for (auto& pc : b->full.classes) {
+        SchwarzArgs A;
+        A.items = pc.d_items;
+        A.n = pc.n;
+        A.la = pc.La;
+        A.lb = pc.Lb;
+        A.ppair = b->full.d_ppair[normalize == SI_NORM_PGTO ? 1 : 0];
+        A.D = D_dev;
+        A.nbf = b->nbf_sph;
+        A.boys = c->boys_dev;
+        A.use_lmn = normalize != SI_NORM_NONE;
+        const int L = pc.La + pc.Lb, M1 = 2 * L + 1, NH = (L + 1) * (L + 2) * (L + 3) / 6;
+        const int ncomp = si_nsph(pc.La) * si_nsph(pc.Lb), e1sz = (pc.La + 1) * (pc.Lb + 1) * (L + 2);
+        const size_t fixed = (size_t)ncomp + M1 + (M1 & 1) + 6 * (size_t)e1sz + 2 * (size_t)M1 * M1 * M1 + (NH + 1) / 2 + 2;
+        const size_t budget = (size_t)c->max_smem / sizeof(double);
+        if (fixed + 2 * (size_t)NH > budget) return SI_ERR_INTERNAL;
+        A.chunk = (int)std::min<size_t>((size_t)ncomp, (budget - fixed) / (2 * (size_t)NH));
+        const size_t smem = (fixed + 2 * (size_t)A.chunk * NH) * sizeof(double);
+        k_schwarz<<<pc.n, 128, smem, s>>>(A);
+        c->launches++;
+        SI_CUDA(cudaGetLastError());
+    }
+    if (Q_dev) {
+        const int n2 = b->nshell * b->nshell;
+        k_schwarz_q<<<(n2 + 127) / 128, 128, 0, s>>>(D_dev, b->nbf_sph, b->nshell, b->d_foff_sph, b->d_L, Q_dev);
+        c->launches++;
+        SI_CUDA(cudaGetLastError());
+    }
+    return mark_done(c, s, SI_OK);
 }
 
 // ---- gto on a grid ------------------------------------------------------------

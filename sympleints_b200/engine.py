@@ -241,6 +241,15 @@ class Engine:
                                     _dp(out), out.size))
         return out
 
+    def schwarz(self, basis, normalize="cgto"):
+        """(D, Q): D[mu, nu] = (mu nu|mu nu) (nbf, nbf) and the shell-pair Schwarz factors Q (nshell, nshell)."""
+        torch = self.torch
+        D = torch.empty((basis.nbf_sph, basis.nbf_sph), dtype=torch.float64, device=self.tdev)
+        Q = torch.empty((basis.nshell, basis.nshell), dtype=torch.float64, device=self.tdev)
+        check(self.lib.si_schwarz(self.ctx, basis.handle, NORMALIZE[normalize], c_void_p(D.data_ptr()), c_void_p(Q.data_ptr()),
+                                  self._stream()))
+        return D, Q
+
     def set_screening(self, eps):
         """Opt-in primitive pre-screening of the 3c2e kernels (0 = off = parity / benchmark mode)."""
         check(self.lib.si_set_screening(self.ctx, float(eps)))

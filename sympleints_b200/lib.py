@@ -54,6 +54,7 @@ SIGNATURES = {
                               c_int, c_double_p, c_double_p, c_double_p,
                               c_int, c_double_p, c_double_p, c_double_p,
                               c_double_p, c_double_p]),
+    "si_schwarz": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "si_set_screening": (c_int, [c_void_p, c_double]),
     "si_host_breakdown": (c_int, [c_void_p, c_double_p]),
     "si_fp64_peak": (c_int, [c_void_p, c_double, c_double_p]),
