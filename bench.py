@@ -390,10 +390,19 @@ def numba_baseline(timeout_s=240):
 
 
 # --------------------------------------------------------------------------------------
-def build_system(natoms):
+AUX_ORDER = "class"
+
+
+def build_system(natoms, aux_order=None):
+    """Orbital and auxiliary shells of the synthetic system.  ``aux_order`` "class" (default): the auxiliary shells
+    sorted by angular momentum (stable; shells.class_major_order) -- a column permutation of the same tensor that
+    the CUDA kernels write faster; "atom": the atom-major order synthetic.aux_basis generates."""
     from sympleints_b200 import synthetic
+    from sympleints_b200.shells import class_major_order
     shells, sites = synthetic.orbital_basis(natoms=natoms)
     aux = synthetic.aux_basis(sites)
+    if (aux_order or AUX_ORDER) == "class":
+        aux = [aux[i] for i in class_major_order(aux)]
     return shells, sites, aux
 
 
@@ -438,6 +447,8 @@ def config_dict(shells, aux, work, world):
                     f"{len(aux)} aux shells / {sum(2 * s.L + 1 for s in aux)} functions (BASELINE configs[4])",
         "integrals_per_step": work["integrals"], "shell_triples": work["triples"],
         "primitive_triples": work["prim_triples"], "model_flops_per_step": work["flops"],
+        "aux_order": "class-major (aux shells sorted by L; columns are a permutation of the atom-major tensor)"
+                     if AUX_ORDER == "class" else "atom-major",
         "parallelism": f"aux-shard x{world} (contiguous cost-balanced aux-shell ranges, no collective)",
         "l2": "every step writes 34 GB / N of output (>> 126 MB L2) and re-reads only ~0.1 MB of shell data and "
               "look-up tables; no explicit flush",
@@ -695,6 +706,23 @@ def run_ours(args, rank, world, local_rank):
                 if k in ("value", "unit", "cores", "kind", "sample")}
         if world == 1 and not args.no_other_keys:
             line["other_keys"] = bench_other_keys(eng, shells, sites, aux, ob, ab, fp64_peak, peaks, args)
+            if AUX_ORDER == "class" and args.shard_of == 1:
+                # the same tensor with the columns in the atom-major order the synthetic generator emits
+                _, _, aux_atom = build_system(args.natoms, "atom")
+                ab2 = eng.basis(aux_atom)
+                out2 = torch.empty((ob.packed_rows, ab2.nbf_sph), dtype=torch.float64, device=eng.tdev)
+                for _ in range(2):
+                    eng.int3c2e(ob, ab2, layout="packed", out=out2)
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(3):
+                    eng.int3c2e(ob, ab2, layout="packed", out=out2)
+                a1.record()
+                torch.cuda.synchronize()
+                line["other_keys"]["3c2e_atom_major_aux_order"] = {"ms_per_step": a0.elapsed_time(a1) / 3,
+                    "note": "same integrals, aux shells in atom-major order (column permutation of the timed tensor)"}
+                del out2
         print(json.dumps(line))
         bad = (parity or {}).get("failed", 0) + ((e2e or {}).get("parity") or {}).get("failed", 0)
         bad += sum((v.get("parity") or {}).get("failed", 0) for v in (line.get("other_keys") or {}).values() if isinstance(v, dict))
@@ -858,8 +886,12 @@ def main():
     ap.add_argument("--no-numba", action="store_true", help="skip the Numba-renderer baseline of the 1e keys")
     ap.add_argument("--numba-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--ref-per-class", type=int, default=16)
+    ap.add_argument("--aux-order", default="class", choices=["class", "atom"],
+                    help="order of the auxiliary shells = column order of the tensor (class: sorted by L)")
     ap.add_argument("--shard-of", type=int, default=1, help="debug: run only rank 0's shard of an N-way partition")
     args = ap.parse_args()
+    global AUX_ORDER
+    AUX_ORDER = args.aux_order
     if args.numba_worker:
         numba_baseline_worker()
         return

@@ -1,8 +1,8 @@
 """Multi-GPU sharding of the 3c2e tensor over auxiliary shells.
 
 Every (ab|c) block is independent, so there is NO collective on the data path: rank r owns a
-contiguous range of auxiliary shells chosen by prefix sums of the per-shell cost model and writes
-its own (rows, naux_local) slab.  Only when a caller asks for the whole tensor on every device is
+contiguous range of the class-major ordered auxiliary shells (plan_aux_shards) chosen by prefix sums of
+the per-shell cost model and writes its own (rows, naux_local) slab.  Only when a caller asks for the whole tensor on every device is
 an all-gather issued (NCCL over NVLink via torch.distributed; gloo on CPU in the tests).
 """
 import numpy as np
@@ -29,6 +29,25 @@ def partition_aux_shells(costs, nranks):
         cuts.append(i)
     cuts.append(n)
     return [(cuts[k], cuts[k + 1]) for k in range(nranks)]
+
+
+def plan_aux_shards(orb_shells, aux_shells, nranks, class_major=True):
+    """Sharding plan of the (ab|c) tensor: ``{"order", "aux", "ranges", "columns", "costs"}``.
+
+    ``order`` permutes the input auxiliary shells (class-major by default, shells.class_major_order: better store
+    locality and 1-2 classes per shard), ``aux`` is the permuted list every rank builds its basis from, ``ranges`` the
+    contiguous shell range of every rank (balanced by the measured-rate cost model, workmodel.aux_shell_costs) and
+    ``columns`` the matching column ranges.  Columns of the distributed tensor follow ``aux``;
+    shells.function_permutation(aux_shells, order) maps them back to the input order."""
+    from . import workmodel
+    from .shells import class_major_order
+
+    order = class_major_order(aux_shells) if class_major else np.arange(len(aux_shells))
+    aux = [aux_shells[i] for i in order]
+    costs = workmodel.aux_shell_costs(orb_shells, aux)
+    ranges = partition_aux_shells(costs, nranks)
+    return {"order": order, "aux": aux, "ranges": ranges, "columns": shard_columns([2 * s.L + 1 for s in aux], ranges),
+            "costs": costs}
 
 
 def shard_columns(aux_sizes, ranges):

@@ -56,3 +56,22 @@ def shells_to_soa(shells):
     exps = np.ascontiguousarray(np.concatenate([s.exps for s in shells]).astype(np.float64))
     coefs = np.ascontiguousarray(np.concatenate([s.coeffs for s in shells]).astype(np.float64))
     return L, nprim, centers, exps, coefs
+
+
+def class_major_order(shells):
+    """Stable permutation that sorts shells by angular momentum ("class-major" order).
+
+    The 3c2e kernels write one (2Lc+1)-wide column chunk per shell triple; with the auxiliary shells of one class
+    adjacent, the chunks of neighbouring tuples fill whole 32-byte sectors and the tensor is written 7 % faster
+    (60.6 vs 65.4 ms on the benchmark system; atom-major order: 14 GB of DRAM read-modify-write traffic per 34 GB
+    written, profiles/r02_final_traffic.json).  A contiguous shard of such a list also holds only one or two classes
+    (15-30 kernel launches instead of 90).  ``[shells[i] for i in order]`` is the reordered list; column block k of a
+    tensor built from it belongs to input shell ``order[k]``."""
+    return np.argsort(np.array([s.L for s in shells]), kind="stable")
+
+
+def function_permutation(shells, order, sph=True):
+    """Index array ``idx`` with ``T_reordered[..., k] == T_input[..., idx[k]]`` for the shell permutation ``order``."""
+    size = [(2 * s.L + 1) if sph else (s.L + 1) * (s.L + 2) // 2 for s in shells]
+    off = np.concatenate([[0], np.cumsum(size)])
+    return np.concatenate([np.arange(off[i], off[i + 1]) for i in order]) if len(order) else np.zeros(0, dtype=int)

@@ -121,8 +121,15 @@ def tensor_3c2e_work(orb_shells, aux_shells, aux_range=None):
                 bytes=8 * integrals, per_class=per_class)
 
 
-def aux_shell_costs(orb_shells, aux_shells):
-    """Model flops attributable to each auxiliary shell (for cost-balanced sharding)."""
+# Measured time per model flop of the generated 3c2e kernels by auxiliary angular momentum Lc, relative to the
+# flop-weighted mean (B200, benchmark system, class-major aux order; scripts/calibrate_lc_weights.py ->
+# profiles/r02_lc_weights.json).  Low Lc runs below the mean rate (fewer integrals per primitive-level recurrence).
+LC_TIME_WEIGHT = (1.374, 1.049, 0.939, 0.911, 0.943, 1.028)
+
+
+def aux_shell_costs(orb_shells, aux_shells, weights=LC_TIME_WEIGHT):
+    """Cost attributable to each auxiliary shell (for cost-balanced sharding): the model flops of all its shell
+    triples, times the measured time-per-flop weight of its angular momentum (``weights=None``: plain flops)."""
     import collections
 
     pair_cls = collections.Counter()
@@ -143,6 +150,6 @@ def aux_shell_costs(orb_shells, aux_shells):
             for (La, Lb), npair in pair_cls.items():
                 fp, fc = flops_3c2e(La, Lb, s.L)
                 c += pair_prims[(La, Lb)] * len(s.exps) * fp + npair * fc
-            cost_by[k] = c
+            cost_by[k] = c * (1.0 if weights is None else weights[s.L])
         out.append(cost_by[k])
     return out

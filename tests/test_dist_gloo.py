@@ -32,6 +32,38 @@ def test_partition_is_contiguous_balanced_and_complete():
     assert sum(p["flops"] for p in parts) == full["flops"]
 
 
+def test_class_major_shard_plan():
+    from sympleints_b200.shells import class_major_order, function_permutation
+
+    shells, sites = synthetic.orbital_basis(natoms=10, seed=3)
+    aux = synthetic.aux_basis(sites, seed=4)
+    plan = sdist.plan_aux_shards(shells, aux, 4)
+    order = plan["order"]
+    assert sorted(order) == list(range(len(aux))) and np.array_equal(order, class_major_order(aux))
+    Ls = [s.L for s in plan["aux"]]
+    assert Ls == sorted(Ls)
+    # stable: shells of one class keep their input order
+    for lc in set(Ls):
+        ks = [k for k in order if aux[k].L == lc]
+        assert ks == sorted(ks)
+    assert plan["ranges"][0][0] == 0 and plan["ranges"][-1][1] == len(aux)
+    assert plan["columns"][-1][1] == sum(2 * s.L + 1 for s in aux)
+    loads = [sum(plan["costs"][b:e]) for b, e in plan["ranges"]]
+    assert max(loads) / (sum(loads) / 4) < 1.06
+    # the measured-rate weights only rescale per class
+    plain = workmodel.aux_shell_costs(shells, plan["aux"], weights=None)
+    assert all(abs(c / p - workmodel.LC_TIME_WEIGHT[s.L]) < 1e-12 for c, p, s in zip(plan["costs"], plain, plan["aux"]))
+    # column map back to the input order
+    idx = function_permutation(aux, order)
+    off = np.concatenate([[0], np.cumsum([2 * s.L + 1 for s in aux])])
+    assert sorted(idx) == list(range(off[-1]))
+    k = order[5]
+    c0 = sum(2 * aux[i].L + 1 for i in order[:5])
+    assert list(idx[c0:c0 + 2 * aux[k].L + 1]) == list(range(off[k], off[k + 1]))
+    same = sdist.plan_aux_shards(shells, aux, 4, class_major=False)
+    assert list(same["order"]) == list(range(len(aux)))
+
+
 def test_benchmark_system_totals_match_survey():
     shells, sites = synthetic.orbital_basis()
     aux = synthetic.aux_basis(sites)

@@ -15,6 +15,7 @@ import pytest
 from oracle import ints, refmod
 from sympleints_b200 import dist as sdist
 from sympleints_b200 import synthetic, workmodel
+from sympleints_b200.shells import class_major_order
 
 pytestmark = pytest.mark.gpu
 
@@ -24,10 +25,11 @@ HAVE_REF = all(refmod.available(k) for k in ("ovlp", "kin", "dpm", "qpm", "dqpm"
 @pytest.fixture(scope="module")
 def system(engine):
     shells, sites = synthetic.orbital_basis(natoms=50)
-    aux = synthetic.aux_basis(sites)
+    aux_atom = synthetic.aux_basis(sites)
+    aux = [aux_atom[i] for i in class_major_order(aux_atom)]   # the order bench.py times (its default --aux-order class)
     assert len(shells) == 300 and sum(2 * s.L + 1 for s in shells) == 1300
     assert len(aux) == 1200 and sum(2 * s.L + 1 for s in aux) == 5000
-    return dict(shells=shells, sites=sites, aux=aux, ob=engine.basis(shells), ab=engine.basis(aux),
+    return dict(shells=shells, sites=sites, aux=aux, aux_atom=aux_atom, ob=engine.basis(shells), ab=engine.basis(aux),
                 offo=np.concatenate([[0], np.cumsum([2 * s.L + 1 for s in shells])]),
                 offa=np.concatenate([[0], np.cumsum([2 * s.L + 1 for s in aux])]))
 
@@ -192,12 +194,14 @@ def test_three_center_tensor_every_rank_shard_of_8(engine, system):
     """Config 5: the slab each of 8 ranks computes (cost-balanced contiguous aux-shell ranges, tuple-table
     kernels where a class has few aux shells in the range), sampled over all classes in the range."""
     shells, aux, ob, ab = system["shells"], system["aux"], system["ob"], system["ab"]
-    ranges = sdist.partition_aux_shells(workmodel.aux_shell_costs(shells, aux), 8)
-    assert ranges[0][0] == 0 and ranges[-1][1] == 1200
+    plan = sdist.plan_aux_shards(shells, system["aux_atom"], 8)
+    ranges = plan["ranges"]
+    assert ranges[0][0] == 0 and ranges[-1][1] == 1200 and [s.L for s in plan["aux"]] == [s.L for s in aux]
+    assert max(len({s.L for s in aux[b:e]}) for b, e in ranges) <= 2      # one or two classes per shard
     nchecked = 0
     for r, (sb, se) in enumerate(ranges):
         T = engine.int3c2e(ob, ab, shell_range=(sb, se), layout="packed")
-        triples = _sample_triples(shells, aux, sb, se, 1, seed=100 + r)[::3]
+        triples = _sample_triples(shells, aux, sb, se, 1, seed=100 + r)
         bad = _check_slab(T, shells, aux, sb, se, triples)
         assert not bad, (r, bad[:5])
         nchecked += len(triples)
@@ -208,7 +212,38 @@ def test_three_center_tensor_every_rank_shard_of_8(engine, system):
             assert np.array_equal(h[idx], T[idx].cpu().numpy())
             assert np.array_equal(h[-1], T[-1].cpu().numpy())
         del T
-    assert nchecked >= 300
+    assert nchecked >= 200
+
+
+def test_three_center_tensor_atom_major_shard_and_column_permutation(engine, system):
+    """The atom-major aux order (every class in every shard, narrow scattered column chunks): rank 5's slab of an
+    8-way partition against the reference, and its columns bit-identical to the same integrals taken from the
+    class-major slabs (the two orders are a column permutation of one tensor)."""
+    shells, aux_atom, ob = system["shells"], system["aux_atom"], system["ob"]
+    ab_atom = engine.basis(aux_atom)
+    sb, se = sdist.partition_aux_shells(workmodel.aux_shell_costs(shells, aux_atom), 8)[5]
+    T = engine.int3c2e(ob, ab_atom, shell_range=(sb, se), layout="packed")
+    triples = _sample_triples(shells, aux_atom, sb, se, 1, seed=77)[::2]
+    bad = _check_slab(T, shells, aux_atom, sb, se, triples)
+    assert not bad, bad[:5]
+    order = class_major_order(aux_atom)
+    inv = np.empty(len(order), dtype=int)
+    inv[order] = np.arange(len(order))
+    offc = system["offa"]
+    offl = np.concatenate([[0], np.cumsum([2 * s.L + 1 for s in aux_atom[sb:se]])])
+    rows = np.random.default_rng(2).integers(0, T.shape[0], 3000)
+    for lc in range(6):    # the shard's shells of one class are contiguous in the class-major basis
+        ks = [k for k in range(sb, se) if aux_atom[k].L == lc]
+        k0, k1 = int(inv[ks[0]]), int(inv[ks[-1]]) + 1
+        assert k1 - k0 == len(ks)
+        C = engine.int3c2e(ob, system["ab"], shell_range=(k0, k1), layout="packed")
+        for n, k in enumerate(ks[:: max(1, len(ks) // 7)]):
+            kk = int(inv[k]) - k0
+            a = T[rows][:, offl[k - sb]:offl[k - sb + 1]]
+            b = C[rows][:, kk * (2 * lc + 1):(kk + 1) * (2 * lc + 1)]
+            assert bool((a == b).all()), (lc, k)
+        del C
+    ab_atom.close()
 
 
 def test_three_center_tensor_full_range_single_gpu(engine, system):
