@@ -670,20 +670,23 @@ def run_ours(args, rank, world, local_rank):
             pass
         tfl = work["flops"] / (ms_per_step * 1e-3) / 1e12 / world   # per GPU
         # DRAM traffic of the kernel family: NOT measured in this run -- read from the committed ncu launch list of the same
-        # command (profiles/r02_final_launches_full.csv, summed over the 90 class launches of one N=1 step)
+        # command (profiles/r02_cm_launches_full.csv for the class-major aux order, r02_final_launches_full.csv for the
+        # atom-major one; summed over the 90 class launches of one N=1 step)
         traffic, traffic_note = None, None
+        tname = "r02_cm" if AUX_ORDER == "class" else "r02_final"
         try:
-            tj = json.loads((REPO / "profiles" / "r02_final_traffic.json").read_text())
+            tj = json.loads((REPO / "profiles" / f"{tname}_traffic.json").read_text())
             if world == 1 and args.shard_of == 1 and args.natoms == 50:
                 traffic = (tj["dram_read_GB_per_step"] + tj["dram_write_GB_per_step"]) * 1e9
                 traffic_note = ("FROM profiles/ (not measured in this run): sum of dram__bytes_read+write over the 90 launches of "
-                                "one step in profiles/r02_final_launches_full.csv; algorithmic bytes per step %.4g" % mywork["bytes"])
+                                f"one step in profiles/{tname}_launches_full.csv (a launch's last dirty L2 lines are written back after it "
+                                "ends and are not in its count); algorithmic bytes per step %.4g" % mywork["bytes"])
         except Exception:
             pass
         roofline = {
             "bound": "fp64", "kernel": "g3_kernel_<La><Lb><Lc> (generated class-specialised 3c2e kernels; every launch of the step is one of the 90 classes, serialised on one stream)",
             "achieved": tfl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tfl / fp64_peak if fp64_peak else None,
-            "traffic": traffic, "traffic_source": "profiles/r02_final_traffic.json" if traffic else None, "traffic_note": traffic_note,
+            "traffic": traffic, "traffic_source": f"profiles/{tname}_traffic.json" if traffic else None, "traffic_note": traffic_note,
             "peak_source": "DFMA microbenchmark si_fp64_peak() measured in this run (FP64 is not in MEASURED_PEAKS.json)",
             "achieved_def": "reference-graph flop model (SURVEY 8d, 88.3 flop/integral) per GPU / CUDA-event step time",
             "hbm_write_GBs": mywork["bytes"] / (ms_per_step * 1e-3) / 1e9,
