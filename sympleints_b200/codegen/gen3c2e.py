@@ -266,15 +266,31 @@ class ClassGen:
         self.Y_OFF = o
         o += self.nm * self.YS
         prim_start = o
-        # primitive temporaries
+        # primitive temporaries.  With Lc > 0 the VRR runs on the scaled quantities binv^n V(n, jn, k) (the scale the aux
+        # recurrence wants: binv folded into PA, CPC and the two (n-2) coefficients), and the lowest-order columns
+        # V(n, 0, :) of all shells ARE the level-0 array of the aux recurrence (flat index off(n) + k): no copy stage.
         self.V_OFF = {}
-        for n in range(L + 1):
-            for jn in range(L - n + 1):
-                self.V_OFF[(n, jn)] = o
-                o += ncart(n)
-        # D-tree arrays per level 0..Lc-1 (non-leaf), flat index relative to off(amin(level))
         self.D_OFF = {}
+        if Lc > 0:
+            for jn in range(L + 1):
+                self.V_OFF[(0, jn)] = o
+                o += 1
+            self.D_OFF[0] = o
+            o += self.NA
+            for n in range(1, L + 1):
+                self.V_OFF[(n, 0)] = self.D_OFF[0] + off(n)
+                for jn in range(1, L - n + 1):
+                    self.V_OFF[(n, jn)] = o
+                    o += ncart(n)
+        else:
+            for n in range(L + 1):
+                for jn in range(L - n + 1):
+                    self.V_OFF[(n, jn)] = o
+                    o += ncart(n)
+        # D-tree arrays per level 1..Lc-1 (non-leaf), flat index relative to off(amin(level))
         for lev in range(0, max(Lc, 1)):
+            if lev in self.D_OFF:
+                continue
             self.D_OFF[lev] = o          # full-size arrays: address of flat index f is D_OFF[lev] + f
             o += self.NA
         prim_end = o
@@ -695,9 +711,13 @@ class ClassGen:
         E("const double pref = 2.0 * SI_PI_25 * rs_ * oop * ocx * Kab * dc;")
         E("// opt-in pre-screening: bound of the squared (ss|s)-type base integral, F_0(T)^2 <= min(1, pi / (4 T)); warp-uniform")
         E("if (A.screen_eps2 > 0.0 && si_g3_warp_all(pref * pref * fmin(1.0, 0.78539816339744831 / fmax(T, 1e-300)) <= A.screen_eps2)) continue;")
-        E("const double oo2p = 0.5 * oop, c2 = -0.5 * oop * rho_p;")
-        E("const double beta = 0.5 * rpc;      // (rho/c)/(2p)")
         E("const double binv = 2.0 * pc_;")
+        if Lc > 0:
+            # VRR on the scaled quantities binv^n V(n): the (n-2) terms pick up binv^2
+            E("const double oo2p = 0.5 * oop * binv * binv, c2 = -rho_p * oo2p;")
+        else:
+            E("const double oo2p = 0.5 * oop, c2 = -0.5 * oop * rho_p;")
+        E("const double beta = 0.5 * rpc;      // (rho/c)/(2p)")
         E("const double rho_c = p * rpc;       // rho / c")
         E("const double alx = rho_c * PC[0], aly = rho_c * PC[1], alz = rho_c * PC[2];")
         E("(void)alx; (void)aly; (void)alz; (void)beta; (void)binv;")
@@ -711,7 +731,10 @@ class ClassGen:
         # scalars to shared memory (lane q==0 of the tuple)
         self.open("if (q == 0)")
         for d in range(3):
-            E(f"W[{self.S_PA + d}] = PA[{d}]; W[{self.S_CPC + d}] = -rho_p * PC[{d}];")
+            if Lc > 0:
+                E(f"W[{self.S_PA + d}] = binv * PA[{d}]; W[{self.S_CPC + d}] = -binv * rho_p * PC[{d}];")
+            else:
+                E(f"W[{self.S_PA + d}] = PA[{d}]; W[{self.S_CPC + d}] = -rho_p * PC[{d}];")
         if Lc > 0 and EPT <= 2:
             E("{ double bp = 1.0;")
             for n in range(L + 1):
@@ -729,9 +752,12 @@ class ClassGen:
         nb = L + 1
         self.open(f"for (int j = q; j < {nb}; j += EPT)")
         if "boys" in SKIP:
-            E(f"W[{self.V_OFF[(0, 0)]} + j] = pref * (T + j);")
+            E(f"const double bv_ = pref * (T + j);")
         else:
-            E(f"W[{self.V_OFF[(0, 0)]} + j] = pref * si_boys_fast(A.boys, {Lc} + j, T);")
+            E(f"const double bv_ = pref * si_boys_fast(A.boys, {Lc} + j, T);")
+        E(f"W[{self.V_OFF[(0, 0)]} + j] = bv_;")
+        if Lc > 0:
+            E(f"if (j == 0) W[{self.D_OFF[0]}] = bv_;   // element 0 of the aux recurrence's level-0 array")
         self.close()
         # note: V(0,jn,0) are contiguous since ncart(0)=1
         for jn in range(nb):
@@ -783,22 +809,7 @@ class ClassGen:
             return
         if "dtree" in SKIP:
             return
-        # root: h[f] = V(n, 0, k) * binv^n for shells amin(0)..L, stored at D_OFF[0] + f
-        self.open("")
-        E("double bq = 1.0;")
-        idx = 0
-        stores = []
-        for n in range(0, L + 1):
-            for s in range(self.nslots(ncart(n))):
-                kk = f"kc_{n}_{s}" if n >= 1 else "0"
-                E(f"const double g{idx}_ = W[{self.V_OFF[(n, 0)]} + {kk}] * bq;")
-                stores.append(f"W[{self.D_OFF[0] + off(n)} + {kk}] = g{idx}_;")
-                idx += 1
-            E("bq *= binv;")
-        for st in stores:
-            E(st)
-        self.close()
-        self.sync()
+        # root: h[f] = V(n, 0, k) * binv^n for shells amin(0)..L is what the scaled VRR left at D_OFF[0] + f
         # DFS over monomials; direction sequences non-decreasing (x.., y.., z..)
         nsl = self.nslots(self.NA)
         # per-slot: own root values + beta powers for the leaves

@@ -104,7 +104,8 @@ def test_own_boys_table_is_accurate():
     eng.close()
     ref = oboys.table()
     assert tab.shape[1] == 301 and tab.shape[0] >= 20
-    np.testing.assert_allclose(tab, ref[: tab.shape[0]], rtol=5e-9)
+    nr = min(tab.shape[0], ref.shape[0])   # own table: orders up to 4 lmax for the Schwarz integrals, the reference's: nmax = 14
+    np.testing.assert_allclose(tab[:nr], ref[:nr], rtol=5e-9)
     for n, i in ((0, 7), (13, 120), (19, 300)):
         np.testing.assert_allclose(tab[n, i], oboys.boys_quad(n, i * 0.1, err=1e-15), rtol=1e-12)
 
