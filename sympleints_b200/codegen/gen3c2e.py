@@ -729,8 +729,16 @@ class ClassGen:
         if L == 0 or Lc == 1:
             self.sync("previous primitive's readers are done")
         # scalars to shared memory (lane q==0 of the tuple)
+        # VRR direction factors: per-lane selects from registers (PASEL) instead of shared-memory scalars
+        pasel = self.PASEL = _os.environ.get("SI_G3_PASEL", "1") == "1" and L >= 1
+        if pasel:
+            sc = "binv * " if Lc > 0 else ""
+            for d in range(3):
+                E(f"const double pas{d}_ = {sc}PA[{d}], cps{d}_ = -{sc}rho_p * PC[{d}];")
         self.open("if (q == 0)")
         for d in range(3):
+            if pasel:
+                continue
             if Lc > 0:
                 E(f"W[{self.S_PA + d}] = binv * PA[{d}]; W[{self.S_CPC + d}] = -binv * rho_p * PC[{d}];")
             else:
@@ -775,7 +783,10 @@ class ClassGen:
             for s in range(nsl_n):
                 # branch-free: lanes beyond the shell recompute (and re-store) its last component
                 E(f"const int m{s}_ = vm_{n}_{s}; const int d{s}_ = m{s}_ & 3; const int k1_{s} = (m{s}_ >> 8) & 0xFF; const int k2_{s} = (m{s}_ >> 16) & 0xFF;")
-                E(f"const double pa{s}_ = W[{self.S_PA} + d{s}_], cp{s}_ = W[{self.S_CPC} + d{s}_];")
+                if pasel:
+                    E(f"const double pa{s}_ = d{s}_ == 0 ? pas0_ : (d{s}_ == 1 ? pas1_ : pas2_), cp{s}_ = d{s}_ == 0 ? cps0_ : (d{s}_ == 1 ? cps1_ : cps2_);")
+                else:
+                    E(f"const double pa{s}_ = W[{self.S_PA} + d{s}_], cp{s}_ = W[{self.S_CPC} + d{s}_];")
                 for jn in range(njn + 1):
                     E(f"const double u{s}_{jn} = W[{self.V_OFF[(n - 1, jn)]} + k1_{s}];")
                     if n >= 2:
