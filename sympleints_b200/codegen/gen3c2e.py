@@ -595,6 +595,11 @@ class ClassGen:
                 E(f"const bool yv_{s} = (q + EPT * {s} >= {off(La)}) && (q + EPT * {s} < {self.NA}); "
                   f"const int yc_{s} = min(max(q + EPT * {s}, {off(La)}), {self.NA - 1}) - {off(La)};")
         E("")
+        # Lanes whose element has no a-1 neighbour read some other element's neighbour slot and multiply it by a zero
+        # factor, and pruned stores leave slots that are read but never written: the tuple's area starts out as zeros
+        # so that every such value is finite.
+        E("for (int i_ = q; i_ < WSZ; i_ += EPT) W[i_] = 0.0;")
+        self.sync()
         if Lb > 0:
             nit_h = self.nca * self.nm
             E("// HRR work items (target a component, m) in the bank-conflict-free order found by the generator:")
@@ -872,7 +877,11 @@ class ClassGen:
                             else:
                                 leaf_updates.append((s, f"W[{ya} + yc_{s}]", coef, f"t{lev2}_{s}"))
                     else:
-                        E(f"W[{self.D_OFF[lev2]} + fc_{s}] = r{lev2}_{s};")
+                        # stored only where the next level reads it as an a-1 neighbour: shells amin(lev2+1)-1 .. L-1
+                        # (the top shell has no reader; about a third of the elements)
+                        f_lo, f_hi = off(max(0, self.amin(lev2 + 1) - 1)), off(L)
+                        if s * EPT < f_hi and s * EPT + EPT - 1 >= f_lo:
+                            E(f"W[{self.D_OFF[lev2]} + fc_{s}] = r{lev2}_{s};")
                 # read-modify-write of the spherical accumulators: all loads, all FMAs, then predicated stores
                 for k_, (s, addr, coef, t) in enumerate(leaf_updates):
                     E(f"const double yo{k_} = {addr};")
