@@ -207,7 +207,32 @@ class ClassGen:
         self.YREG = Lc > 0 and self.nm * len(tslots) <= ymax
         self.lines = []
         self.ind = 1
+        # Lane-private start of the VRR ("chain"): shells 1..N0 are built by the lanes that own the components of shell
+        # N0 (the largest shell that fits one slot), each along its own path z..z y..y x..x from shell 0, all Boys orders
+        # in registers -- the same FP64 instruction count as one staged slot per shell, but no shared-memory round trips
+        # and no barriers in between.  Lower shells are stored only where a later stage reads them.
+        n0 = 0
+        if _os.environ.get("SI_G3_CHAIN", "1") == "1" and "vrr" not in SKIP:
+            for n in range(1, L + 1):
+                if ncart(n) <= ept:
+                    n0 = n
+        self.N0 = n0 if n0 >= 2 else 0
         self._layout()
+
+    def chain_stores(self):
+        """{shell n < N0: number of orders jn to store} for the lower shells of the chain (empty entries left out)."""
+        L, n0 = self.L, self.N0
+        need_lo = self.amin(0) if self.Lc > 0 else self.La     # lowest shell whose order-0 column is read later
+        out = {}
+        for n in range(1, n0):
+            cnt = 0
+            if n >= need_lo:
+                cnt = 1
+            if n == n0 - 1 and L > n0:
+                cnt = L - n0 + 1          # the (n-2) operand of the first staged shell N0+1, orders 0..L-N0
+            if cnt:
+                out[n] = cnt
+        return out
 
     def has_table_variant(self):
         """Classes with >= 4 tuples per warp also get a kernel that takes its tuples from a host-built table."""
@@ -277,14 +302,20 @@ class ClassGen:
                 o += 1
             self.D_OFF[0] = o
             o += self.NA
+            cs = self.chain_stores()
             for n in range(1, L + 1):
                 self.V_OFF[(n, 0)] = self.D_OFF[0] + off(n)
                 for jn in range(1, L - n + 1):
+                    if n < self.N0 and jn >= cs.get(n, 0):
+                        continue         # lives in the registers of the lane-private chain only
                     self.V_OFF[(n, jn)] = o
                     o += ncart(n)
         else:
+            cs = self.chain_stores()
             for n in range(L + 1):
                 for jn in range(L - n + 1):
+                    if 1 <= n < self.N0 and jn >= cs.get(n, 0):
+                        continue
                     self.V_OFF[(n, jn)] = o
                     o += ncart(n)
         # D-tree arrays per level 1..Lc-1 (non-leaf), flat index relative to off(amin(level))
@@ -542,6 +573,14 @@ class ClassGen:
         for n in range(1, L + 1):
             vals = [d | (fac << 2) | (k1 << 8) | (k2 << 16) for (d, k1, k2, fac) in vm[n]]
             E(f"__device__ const int g3_vrr_{name}_{n}[{len(vals)}] = {{{', '.join(map(str, vals))}}};")
+        if self.N0:
+            comps = cart_order(self.N0)
+            vals = [a[0] | (a[1] << 4) | (a[2] << 8) for a in comps]
+            E(f"__device__ const int g3_pc_{name}[{len(vals)}] = {{{', '.join(map(str, vals))}}};")
+            for n in self.chain_stores():
+                k = self.N0 - n
+                vals = [cidx((a[0] - k, a[1], a[2])) if a[0] >= k else -1 for a in comps]
+                E(f"__device__ const int g3_pci_{name}_{n}[{len(vals)}] = {{{', '.join(map(str, vals))}}};")
         if Lc > 0:
             # D-tree: per flat index: byte... element deltas (<=0) packed 3x10 bits (as positive magnitudes), shell, factors 3x4 bits
             vals = []
@@ -584,6 +623,11 @@ class ClassGen:
         for n in range(1, L + 1):
             for s in range(nsl_v[n]):
                 E(f"const int kc_{n}_{s} = min(q + EPT * {s}, {ncart(n) - 1}); const int vm_{n}_{s} = g3_vrr_{name}_{n}[kc_{n}_{s}];")
+        if self.N0:
+            n0 = self.N0
+            E(f"const int pk_ = g3_pc_{name}[kc_{n0}_0]; const int cay_ = (pk_ >> 4) & 15, caz_ = pk_ >> 8; (void)cay_; (void)caz_;")
+            for n in self.chain_stores():
+                E(f"const int ci_{n} = g3_pci_{name}_{n}[kc_{n0}_0];")
         nsl_d = self.nslots(self.NA)
         if Lc > 0:
             for s in range(nsl_d):
@@ -776,8 +820,37 @@ class ClassGen:
         for jn in range(nb):
             assert self.V_OFF[(0, jn)] == self.V_OFF[(0, 0)] + jn
         self.sync()
+        # ---- lane-private chain over shells 1..N0
+        n0 = self.N0
+        if n0:
+            assert pasel
+            self.open("")
+            for jn in range(L + 1):
+                E(f"const double c0_{jn} = W[{self.V_OFF[(0, jn)]}];")
+            cs = self.chain_stores()
+            stores = []
+            for k in range(1, n0 + 1):
+                E(f"const int cd{k}_ = {k} <= caz_ ? 2 : ({k} <= caz_ + cay_ ? 1 : 0);")
+                E(f"const double pa{k}_ = cd{k}_ == 0 ? pas0_ : (cd{k}_ == 1 ? pas1_ : pas2_), cp{k}_ = cd{k}_ == 0 ? cps0_ : (cd{k}_ == 1 ? cps1_ : cps2_);")
+                if k >= 2:
+                    E(f"const double cf{k}_ = (double)(cd{k}_ == 2 ? {k - 1} : (cd{k}_ == 1 ? {k - 1} - caz_ : {k - 1} - caz_ - cay_));")
+                    E(f"const double f1{k}_ = cf{k}_ * oo2p, f2{k}_ = cf{k}_ * c2;")
+                for jn in range(L - k + 1):
+                    if k >= 2:
+                        E(f"const double c{k}_{jn} = fma(f2{k}_, c{k - 2}_{jn + 1}, fma(f1{k}_, c{k - 2}_{jn}, fma(pa{k}_, c{k - 1}_{jn}, cp{k}_ * c{k - 1}_{jn + 1})));")
+                    else:
+                        E(f"const double c{k}_{jn} = fma(pa{k}_, c{k - 1}_{jn}, cp{k}_ * c{k - 1}_{jn + 1});")
+                if k < n0 and k in cs:
+                    for jn in range(cs[k]):
+                        stores.append(f"if (ci_{k} >= 0) W[{self.V_OFF[(k, jn)]} + ci_{k}] = c{k}_{jn};")
+            for jn in range(L - n0 + 1):
+                stores.append(f"W[{self.V_OFF[(n0, jn)]} + kc_{n0}_0] = c{n0}_{jn};")
+            for st in stores:
+                E(st)
+            self.close()
+            self.sync()
         # ---- VRR shells
-        for n in range(1, (0 if "vrr" in SKIP else L) + 1):
+        for n in range(n0 + 1, (0 if "vrr" in SKIP else L) + 1):
             nc = ncart(n)
             njn = L - n + 1
             # Shared-memory loads and stores of one stage touch disjoint arrays, but the compiler cannot
