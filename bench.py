@@ -670,10 +670,10 @@ def run_ours(args, rank, world, local_rank):
             pass
         tfl = work["flops"] / (ms_per_step * 1e-3) / 1e12 / world   # per GPU
         # DRAM traffic of the kernel family: NOT measured in this run -- read from the committed ncu launch list of the same
-        # command (profiles/r02_cm_launches_full.csv for the class-major aux order, r02_final_launches_full.csv for the
+        # command (profiles/r02_end_launches_full.csv for the class-major aux order, r02_final_launches_full.csv for the
         # atom-major one; summed over the 90 class launches of one N=1 step)
         traffic, traffic_note = None, None
-        tname = "r02_cm" if AUX_ORDER == "class" else "r02_final"
+        tname = "r02_end" if AUX_ORDER == "class" else "r02_final"
         try:
             tj = json.loads((REPO / "profiles" / f"{tname}_traffic.json").read_text())
             if world == 1 and args.shard_of == 1 and args.natoms == 50:
