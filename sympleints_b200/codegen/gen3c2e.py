@@ -623,11 +623,19 @@ class ClassGen:
         for n in range(1, L + 1):
             for s in range(nsl_v[n]):
                 E(f"const int kc_{n}_{s} = min(q + EPT * {s}, {ncart(n) - 1}); const int vm_{n}_{s} = g3_vrr_{name}_{n}[kc_{n}_{s}];")
+                if n >= 2 and n > self.N0:
+                    # (n-2) factor of the staged shells as a per-lane constant (the int -> double conversion is slow)
+                    E(f"const double vf_{n}_{s} = (double)((vm_{n}_{s} >> 2) & 0xF);")
         if self.N0:
             n0 = self.N0
             E(f"const int pk_ = g3_pc_{name}[kc_{n0}_0]; const int cay_ = (pk_ >> 4) & 15, caz_ = pk_ >> 8; (void)cay_; (void)caz_;")
             for n in self.chain_stores():
                 E(f"const int ci_{n} = g3_pci_{name}_{n}[kc_{n0}_0];")
+            # direction and (n-2) factor of every chain step: per-lane constants of the kernel
+            for k in range(1, n0 + 1):
+                E(f"const int cd{k}_ = {k} <= caz_ ? 2 : ({k} <= caz_ + cay_ ? 1 : 0);")
+                if k >= 2:
+                    E(f"const double cf{k}_ = (double)(cd{k}_ == 2 ? {k - 1} : (cd{k}_ == 1 ? {k - 1} - caz_ : {k - 1} - caz_ - cay_));")
         nsl_d = self.nslots(self.NA)
         if Lc > 0:
             for s in range(nsl_d):
@@ -830,10 +838,8 @@ class ClassGen:
             cs = self.chain_stores()
             stores = []
             for k in range(1, n0 + 1):
-                E(f"const int cd{k}_ = {k} <= caz_ ? 2 : ({k} <= caz_ + cay_ ? 1 : 0);")
                 E(f"const double pa{k}_ = cd{k}_ == 0 ? pas0_ : (cd{k}_ == 1 ? pas1_ : pas2_), cp{k}_ = cd{k}_ == 0 ? cps0_ : (cd{k}_ == 1 ? cps1_ : cps2_);")
                 if k >= 2:
-                    E(f"const double cf{k}_ = (double)(cd{k}_ == 2 ? {k - 1} : (cd{k}_ == 1 ? {k - 1} - caz_ : {k - 1} - caz_ - cay_));")
                     E(f"const double f1{k}_ = cf{k}_ * oo2p, f2{k}_ = cf{k}_ * c2;")
                 for jn in range(L - k + 1):
                     if k >= 2:
@@ -871,7 +877,7 @@ class ClassGen:
                         E(f"const double w{s}_{jn} = W[{self.V_OFF[(n - 2, jn)]} + k2_{s}];")
             for s in range(nsl_n):
                 if n >= 2:
-                    E(f"const double fc{s}_ = (double)((m{s}_ >> 2) & 0xF); const double f1_{s} = fc{s}_ * oo2p, f2_{s} = fc{s}_ * c2;")
+                    E(f"const double f1_{s} = vf_{n}_{s} * oo2p, f2_{s} = vf_{n}_{s} * c2;")
                 for jn in range(njn):
                     if n >= 2:
                         E(f"const double v{s}_{jn} = fma(f2_{s}, w{s}_{jn + 1}, fma(f1_{s}, w{s}_{jn}, fma(pa{s}_, u{s}_{jn}, cp{s}_ * u{s}_{jn + 1})));")
