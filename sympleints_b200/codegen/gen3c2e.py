@@ -675,7 +675,7 @@ class ClassGen:
         E("// padding (recomputes the group's first tuple).")
         E("int2 t_ = TAB ? A.tuples[grp * TPW + tl] : int2{0, 0};")
         E("if (TAB && t_.x < 0) t_ = A.tuples[grp * TPW];")
-        E("const int ip = TAB ? t_.x : (int)(grp / A.groups_per_pair);")
+        E("const int ip = TAB ? t_.x : (int)((unsigned)grp / (unsigned)A.groups_per_pair);   // group indices fit 31 bits (32-bit work counter; checked by the host)")
         E("const int gi = (int)(grp - (long long)ip * A.groups_per_pair);")
         E("int ic = TAB ? t_.y : gi * TPW + tl;")
         E("const bool valid = TAB ? (A.tuples[grp * TPW + tl].x >= 0) : (ic < A.naux_c);")

@@ -1908,6 +1908,11 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
                     ga.ngroups = tt->ngroups;
                 }
             }
+            if (ga.ngroups >= (1ll << 31) - 65536) {
+                // 32-bit work counter and group arithmetic in the kernels (2^31 groups = ~1e10 shell triples of one class)
+                g_last_error = "too many shell tuples in one class for one call: split the auxiliary range";
+                return SI_ERR_ARG;
+            }
             int grid, block;
             size_t smem;
             if (!g3_config(c, g3, ga.ngroups, &grid, &block, &smem)) {
