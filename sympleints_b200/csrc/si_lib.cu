@@ -307,6 +307,40 @@ __global__ void __launch_bounds__(256) k_mirror_lower(double* m, long long n) {
     }
 }
 
+// The same for a matrix of which only the shell blocks with L(row shell) >= L(column shell) were computed (2c2e through
+// the (a s0|b) classes with La >= Lb): element (r, c) := element (c, r) where L(r) < L(c), or L(r) == L(c) and c > r.
+__global__ void __launch_bounds__(256) k_mirror_by_l(double* m, long long n, const signed char* fnL) {
+    __shared__ double tile[32][33];
+    __shared__ int need;
+    const int bi = blockIdx.y, bj = blockIdx.x;   // tile (bi, bj) is (partly) written from tile (bj, bi)
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (threadIdx.x == 0) need = 0;
+    __syncthreads();
+    const long long col = (long long)bj * 32 + tx;
+    const int lc = col < n ? fnL[col] : 127;
+    bool take[4];
+    for (int k = 0; k < 4; ++k) {
+        const long long row = (long long)bi * 32 + ty + 8 * k;
+        take[k] = false;
+        if (row < n && col < n) {
+            const int lr = fnL[row];
+            take[k] = lr < lc || (lr == lc && col > row);
+        }
+        if (take[k]) need = 1;
+    }
+    __syncthreads();
+    if (!need) return;
+    for (int r = ty; r < 32; r += 8) {
+        const long long row = (long long)bj * 32 + r, c2 = (long long)bi * 32 + tx;   // source tile (bj, bi)
+        if (row < n && c2 < n) tile[r][tx] = m[row * n + c2];
+    }
+    __syncthreads();
+    for (int k = 0; k < 4; ++k) {
+        const int r = ty + 8 * k;
+        if (take[k]) m[((long long)bi * 32 + r) * n + col] = tile[tx][r];
+    }
+}
+
 // mode 0: si_boys (the reference's summation order); 1: si_boys_fast, the variant every generated 3c2e kernel
 // calls (Horner/FMA Taylor sum on the transposed table, binary-power asymptote); 2: the variant of the generated
 // nuclear-attraction kernels (one shared rsqrt per charge, prefactor kept in a register)
@@ -433,6 +467,7 @@ struct si_context {
     // (device arrays are uploaded again, the shell-batcher's pair sets / tuple tables / aux lists are kept)
     std::vector<struct si_basis*> basis_cache;   // least recently used first
     std::map<size_t, int> onee_occ;              // resident blocks per SM of k_onee by dynamic shared-memory size
+    bool twoc_lower_only = false;                // si_int2c2e: evaluate the classes with La >= Lb only
     bool capturing = false;                      // a call is being captured into a CUDA graph (no ev_last traffic)
     double screen_eps = 0.0;                     // opt-in primitive pre-screening threshold of the 3c2e kernels (0 = off)
 };
@@ -509,6 +544,7 @@ struct si_basis {
     // 2c2e through the generated 3c2e kernels: (a|b) = (a s0|b) with a unit s shell of exponent 0
     mutable si_basis* twoc_orb = nullptr;     // copy of this basis + the s0 shell (last)
     mutable PairSet* twoc_pairs = nullptr;    // pairs (shell j, s0)
+    mutable signed char* d_fn_L = nullptr;    // angular momentum of every spherical function (2c2e mirror)
     // The metric is ~36 short class launches + the mirror kernel: launch-rate bound when issued one by one.  After
     // a first ordinary call (which fills every cache) the call sequence is captured into a CUDA graph per
     // (output pointer, normalisation) and replayed with one cudaGraphLaunch.
@@ -950,6 +986,7 @@ static void basis_free(si_basis* b) {
     cudaFree(b->d_coef);
     cudaFree(b->d_coef_pgto);
     cudaFree(b->d_oexp);
+    if (b->d_fn_L) cudaFree(b->d_fn_L);
     if (b->twoc_pairs) {
         free_pair_set(b->twoc_pairs);
         delete b->twoc_pairs;
@@ -1463,13 +1500,25 @@ int si_int2c2e(si_context* c, const si_basis* b, int sph, int normalize, double*
         b->twoc_orb = tb;
         b->twoc_pairs = ps;
     }
+    if (!b->d_fn_L) {
+        std::vector<signed char> fl((size_t)b->nbf_sph);
+        for (int sh = 0; sh < b->nshell; ++sh)
+            for (int m = 0; m < si_nsph(b->L[sh]); ++m) fl[(size_t)b->foff_sph[sh] + m] = (signed char)b->L[sh];
+        SI_CUDA(cudaMalloc(&b->d_fn_L, fl.size()));
+        SI_CUDA(cudaMemcpy(b->d_fn_L, fl.data(), fl.size(), cudaMemcpyHostToDevice));
+        SI_CUDA(cudaDeviceSynchronize());
+    }
     const size_t n = (size_t)b->nbf_sph;
     cudaStream_t user = (cudaStream_t)stream;
     auto enqueue = [&]() -> int {
+        // only the classes (La s0|Lb) with La >= Lb are evaluated (21 of the 36 for lauxmax = 5); the other blocks are
+        // their transposes.  Source and destination elements of the mirror are disjoint, so it runs in place.
+        c->twoc_lower_only = true;
         int rc = int3c2e_impl(c, b->twoc_orb, b, 0, b->nshell, normalize, SI_LAYOUT_PACKED, b->twoc_pairs, out_dev, n * n, stream);
+        c->twoc_lower_only = false;
         if (rc) return rc;
         const unsigned nt = (unsigned)((n + 31) / 32);
-        k_mirror_lower<<<dim3(nt, nt), 256, 0, user>>>(out_dev, (long long)n);
+        k_mirror_by_l<<<dim3(nt, nt), 256, 0, user>>>(out_dev, (long long)n, b->d_fn_L);
         c->launches++;
         SI_CUDA(cudaGetLastError());
         return SI_OK;
@@ -1851,6 +1900,7 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
     std::vector<Job> jobs;
     for (auto& pc : pset->classes)
         for (auto& kv : span) {
+            if (c->twoc_lower_only && kv.first > pc.La) continue;   // 2c2e: (a|b) blocks with La < Lb come from the mirror
             DevProgram* p;
             rc = get_program(c, SI_3C2E, pc.La, pc.Lb, kv.first, 1, normalize, &p);
             if (rc) return rc;
