@@ -467,6 +467,7 @@ struct si_context {
     // (device arrays are uploaded again, the shell-batcher's pair sets / tuple tables / aux lists are kept)
     std::vector<struct si_basis*> basis_cache;   // least recently used first
     std::map<size_t, int> onee_occ;              // resident blocks per SM of k_onee by dynamic shared-memory size
+    bool small_call = false;                     // int3c2e_impl: the current call is launch-latency bound (see g3_config)
     bool twoc_lower_only = false;                // si_int2c2e: evaluate the classes with La >= Lb only
     bool capturing = false;                      // a call is being captured into a CUDA graph (no ev_last traffic)
     double screen_eps = 0.0;                     // opt-in primitive pre-screening threshold of the 3c2e kernels (0 = off)
@@ -1661,6 +1662,7 @@ static int run_coul_generated(si_context* c, const si_basis* cb, int normalize, 
         ga.boys = c->boys_dev;
         int grid, block;
         size_t smem;
+        c->small_call = false;
         if (!g3_config(c, gc, ga.ngroups, &grid, &block, &smem)) return SI_ERR_INTERNAL;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (profile) {
@@ -1764,7 +1766,9 @@ static bool g3_config(const si_context* c, const int* g3, long long ngroups, int
     if (nw < 1) return false;
     *block = nw * 32;
     *smem = per_warp * nw;
-    const int per_sm = si_env().g3_grid_per_sm;   // persistent blocks: at most 4 x 4 warps are resident per SM
+    // persistent blocks: at most 4 x 4 warps are resident per SM.  A call that is small as a whole (the 2c2e metric) fans
+    // its launches out over all streams; one block per SM each lets them run side by side (330 -> 290 us for the metric)
+    const int per_sm = c->small_call ? 1 : si_env().g3_grid_per_sm;
     *grid = (int)std::max<long long>(1, std::min<long long>((ngroups + nw - 1) / nw, (long long)c->sm_count * per_sm * (4 / nw)));
     return true;
 }
@@ -1919,7 +1923,11 @@ static int int3c2e_impl(si_context* c, const si_basis* corb, const si_basis* cau
         use_pdl = si_env().pdl < 0 ? (2.0 * total < si_env().g3_pdl_total && 2.0 * total >= si_env().g3_small_total)
                                    : si_env().pdl != 0;
         fan.limit = use_pdl ? 1 : si_env().g3_fan;
-        if (2.0 * total < si_env().g3_small_total && !use_pdl) fan.limit = SI_NSTREAMS;
+        c->small_call = false;
+        if (2.0 * total < si_env().g3_small_total && !use_pdl) {
+            fan.limit = SI_NSTREAMS;
+            c->small_call = true;
+        }
     }
     for (auto& job : jobs) {
         DevProgram* p;
