@@ -2039,12 +2039,16 @@ int si_schwarz(si_context* c, const si_basis* cb, int normalize, double* D_dev, 
         A.use_lmn = normalize != SI_NORM_NONE;
         const int L = pc.La + pc.Lb, M1 = 2 * L + 1, NH = (L + 1) * (L + 2) * (L + 3) / 6;
         const int ncomp = si_nsph(pc.La) * si_nsph(pc.Lb), e1sz = (pc.La + 1) * (pc.Lb + 1) * (L + 2);
-        const size_t fixed = (size_t)ncomp + M1 + (M1 & 1) + 6 * (size_t)e1sz + 2 * (size_t)M1 * M1 * M1 + (NH + 1) / 2 + 2;
+        const int NW = (NH + 31) / 32;
+        const size_t fixed = (size_t)ncomp + M1 + (M1 & 1) + 6 * (size_t)e1sz + 2 * (size_t)M1 * M1 * M1 + (size_t)NH + 4;
         const size_t budget = (size_t)c->max_smem / sizeof(double);
-        if (fixed + 2 * (size_t)NH > budget) return SI_ERR_INTERNAL;
-        A.chunk = (int)std::min<size_t>((size_t)ncomp, (budget - fixed) / (2 * (size_t)NH));
-        const size_t smem = (fixed + 2 * (size_t)A.chunk * NH) * sizeof(double);
-        k_schwarz<<<pc.n, 128, smem, s>>>(A);
+        const size_t per_comp = 2 * (size_t)NH + NW;
+        if (fixed + per_comp > budget) return SI_ERR_INTERNAL;
+        A.chunk = (int)std::min<size_t>((size_t)ncomp, (budget - fixed) / per_comp);
+        const size_t smem = (fixed + (size_t)A.chunk * per_comp) * sizeof(double);
+        // threads per shell pair: the work items of the two heavy stages are (component pair, Hermite index)
+        const int nthr = (size_t)ncomp * NH >= 4096 ? 512 : ((size_t)ncomp * NH >= 512 ? 256 : 128);
+        k_schwarz<<<pc.n, nthr, smem, s>>>(A);
         c->launches++;
         SI_CUDA(cudaGetLastError());
     }

@@ -40,7 +40,7 @@ __device__ __forceinline__ void schwarz_e1d(double* e, int la, int lb, int ts, d
             }
 }
 
-__global__ void __launch_bounds__(128) k_schwarz(SchwarzArgs A) {
+__global__ void __launch_bounds__(512) k_schwarz(SchwarzArgs A) {
     extern __shared__ double sm[];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int la = A.la, lb = A.lb, L = la + lb, M = 2 * L, M1 = M + 1;
@@ -56,11 +56,18 @@ __global__ void __launch_bounds__(128) k_schwarz(SchwarzArgs A) {
     double* Ra = EQ + CH * NH;               // [M1^3]
     double* Rb = Ra + M1 * M1 * M1;
     int* hl = reinterpret_cast<int*>(Rb + M1 * M1 * M1);   // NH packed (t | u << 8 | v << 16)
+    int* hb = hl + NH;                                      // NH: offset of (t, u, v) in an R cube | odd parity << 31
+    const int NW = (NH + 31) / 32;                          // warps (of 32 Hermite indices) per component pair
+    double* part = reinterpret_cast<double*>(hb + NH);               // [CH][NW] partial sums of the bilinear form
     if (tid == 0) {
         int h = 0;
         for (int t = 0; t <= L; ++t)
             for (int u = 0; u <= L - t; ++u)
-                for (int v = 0; v <= L - t - u; ++v) hl[h++] = t | (u << 8) | (v << 16);
+                for (int v = 0; v <= L - t - u; ++v) {
+                    hl[h] = t | (u << 8) | (v << 16);
+                    hb[h] = ((t * M1 + u) * M1 + v) | (((t + u + v) & 1) << 31);
+                    ++h;
+                }
     }
     for (int i = tid; i < ncomp; i += nthr) acc[i] = 0.0;
     const SiPairItem it = A.items[blockIdx.x];
@@ -151,23 +158,40 @@ __global__ void __launch_bounds__(128) k_schwarz(SchwarzArgs A) {
                 }
                 const double* R0 = prev;   // level 0
                 const double pref = 2.0 * SI_PI_25 / (p * q * sqrt(p + q)) * (ipQ == ipP ? 1.0 : 2.0);
-                for (int c = tid; c < nc; c += nthr) {
-                    const double* e1 = EP + c * NH;
-                    const double* e2 = EQp + c * NH;
-                    double s = 0.0;
-                    for (int h = 0; h < NH; ++h) {
-                        const double a1 = e1[h];
-                        if (a1 == 0.0) continue;
-                        const int t = hl[h] & 255, u = (hl[h] >> 8) & 255, v = hl[h] >> 16;
-                        double in = 0.0;
-                        for (int g = 0; g < NH; ++g) {
-                            const int t2 = hl[g] & 255, u2 = (hl[g] >> 8) & 255, v2 = hl[g] >> 16;
-                            const double r = R0[((t + t2) * M1 + u + u2) * M1 + v + v2];
-                            in = ((t2 + u2 + v2) & 1) ? fma(-r, e2[g], in) : fma(r, e2[g], in);
+                // bilinear form: work items (component pair c, Hermite index h), the 32 lanes of a warp hold consecutive h of
+                // one c; the inner sum over h' reads R (gather), E^Q (broadcast) and the packed offsets (broadcast)
+                for (int item = tid; item < nc * NW * 32; item += nthr) {
+                    const int c = item / (NW * 32), h = item - c * (NW * 32);
+                    double sh = 0.0;
+                    if (h < NH) {
+                        const double a1 = EP[c * NH + h];
+                        if (a1 != 0.0) {
+                            const double* e2 = EQp + c * NH;
+                            const double* Rh = R0 + (hb[h] & 0x7fffffff);
+                            double i0 = 0.0, i1 = 0.0;
+                            int g = 0;
+                            for (; g + 1 < NH; g += 2) {
+                                const int w0 = hb[g], w1 = hb[g + 1];
+                                const double r0 = Rh[w0 & 0x7fffffff], r1 = Rh[w1 & 0x7fffffff];
+                                i0 = fma(w0 < 0 ? -r0 : r0, e2[g], i0);
+                                i1 = fma(w1 < 0 ? -r1 : r1, e2[g + 1], i1);
+                            }
+                            if (g < NH) {
+                                const int w0 = hb[g];
+                                const double r0 = Rh[w0 & 0x7fffffff];
+                                i0 = fma(w0 < 0 ? -r0 : r0, e2[g], i0);
+                            }
+                            sh = a1 * (i0 + i1);
                         }
-                        s = fma(a1, in, s);
                     }
-                    acc[c0 + c] += pref * s;
+                    for (int o = 16; o > 0; o >>= 1) sh += __shfl_xor_sync(0xffffffffu, sh, o);
+                    if ((tid & 31) == 0) part[c * NW + (h >> 5)] = sh;
+                }
+                __syncthreads();
+                for (int c = tid; c < nc; c += nthr) {
+                    double sc = 0.0;
+                    for (int w = 0; w < NW; ++w) sc += part[c * NW + w];
+                    acc[c0 + c] += pref * sc;
                 }
                 __syncthreads();
             }
