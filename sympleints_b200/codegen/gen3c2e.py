@@ -212,7 +212,7 @@ class ClassGen:
         # in registers -- the same FP64 instruction count as one staged slot per shell, but no shared-memory round trips
         # and no barriers in between.  Lower shells are stored only where a later stage reads them.
         n0 = 0
-        if _os.environ.get("SI_G3_CHAIN", "1") == "1" and "vrr" not in SKIP:
+        if _os.environ.get("SI_G3_CHAIN", "1") == "1" and _os.environ.get("SI_G3_PASEL", "1") == "1" and "vrr" not in SKIP:
             for n in range(1, L + 1):
                 if ncart(n) <= ept:
                     n0 = n
