@@ -690,6 +690,10 @@ class ClassGen:
         if self.YREG:
             for m in range(self.nm):
                 E("double " + ", ".join(f"ya_{m}_{s} = 0.0" for s in self.tslots) + ";   // contraction accumulators (registers)")
+        elif Lc == 0 and Y0REG:
+            # s-type aux shell: Y[0][a'] accumulates V(n, 0, k) of the shells La..L, per (shell, slot) in registers
+            self.y0 = [(n, s_) for n in range(La, L + 1) for s_ in range(self.nslots(ncart(n)))]
+            E("double " + ", ".join(f"y0_{n}_{s_} = 0.0" for (n, s_) in self.y0) + ";   // contraction accumulators (registers)")
         else:
             E(f"for (int i_ = q; i_ < {self.nm * self.YS}; i_ += EPT) W[{self.Y_OFF} + i_] = 0.0;   // contraction accumulator")
         self.open("for (int ia = 0; ia < Ka; ++ia)")
@@ -716,6 +720,11 @@ class ClassGen:
         E("// its round trip overlaps the contracted phase.  (Issued earlier, the result register gets spilled, and")
         E("// the spill store waits for the atomic.)")
         E("const int ch_raw = si_g3_fetch_group(A.counter, lane);")
+        if Lc == 0 and Y0REG:
+            self.sync("last primitive's readers of the overlaid arrays are done")
+            for (n, s_) in self.y0:
+                kk = f"kc_{n}_{s_}" if n >= 1 else "0"
+                E(f"W[{self.Y_OFF + off(n) - off(La)} + {kk}] = y0_{n}_{s_};")
         if self.YREG:
             self.sync("last primitive's readers of the overlaid arrays are done")
             for m in range(self.nm):
@@ -849,8 +858,13 @@ class ClassGen:
                 if k < n0 and k in cs:
                     for jn in range(cs[k]):
                         stores.append(f"if (ci_{k} >= 0) W[{self.V_OFF[(k, jn)]} + ci_{k}] = c{k}_{jn};")
+            y0direct = Lc == 0 and Y0REG
             for jn in range(L - n0 + 1):
+                if y0direct and n0 == L:
+                    continue          # top shell of an s-type aux class: goes straight into the register accumulator
                 stores.append(f"W[{self.V_OFF[(n0, jn)]} + kc_{n0}_0] = c{n0}_{jn};")
+            if y0direct and n0 >= La:
+                E(f"y0_{n0}_0 += c{n0}_0;")
             for st in stores:
                 E(st)
             self.close()
@@ -883,12 +897,24 @@ class ClassGen:
                         E(f"const double v{s}_{jn} = fma(f2_{s}, w{s}_{jn + 1}, fma(f1_{s}, w{s}_{jn}, fma(pa{s}_, u{s}_{jn}, cp{s}_ * u{s}_{jn + 1})));")
                     else:
                         E(f"const double v{s}_{jn} = fma(pa{s}_, u{s}_{jn}, cp{s}_ * u{s}_{jn + 1});")
+            y0direct = Lc == 0 and Y0REG
             for s in range(nsl_n):
+                if y0direct and n >= La:
+                    E(f"y0_{n}_{s} += v{s}_0;")
                 for jn in range(njn):
+                    if y0direct and n == L:
+                        continue      # top shell: nobody reads it from shared memory
                     E(f"W[{self.V_OFF[(n, jn)]} + kc_{n}_{s}] = v{s}_{jn};")
             self.close()
             self.sync()
         # ---- D-tree
+        if Lc == 0 and Y0REG:
+            for (n, s_) in self.y0:
+                if n >= max(self.N0, 1) and "vrr" not in SKIP:
+                    continue          # accumulated from the registers of its VRR stage
+                kk = f"kc_{n}_{s_}" if n >= 1 else "0"
+                E(f"y0_{n}_{s_} += W[{self.V_OFF[(n, 0)]} + {kk}];")
+            return
         if Lc == 0:
             # Y[0][a'] (+)= V(n,0,k) for shells La..L   (C2S of an s function is the identity)
             for n in range(La, L + 1):
@@ -1080,6 +1106,8 @@ class ClassGen:
         self.close()
         self.close()
 
+
+Y0REG = _os.environ.get("SI_G3_Y0REG", "1") == "1"
 
 HEADER = """// GENERATED by sympleints_b200/codegen/gen3c2e.py -- DO NOT EDIT.
 #include "../si_g3.h"
