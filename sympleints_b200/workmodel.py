@@ -124,7 +124,7 @@ def tensor_3c2e_work(orb_shells, aux_shells, aux_range=None):
 # Measured time per model flop of the generated 3c2e kernels by auxiliary angular momentum Lc, relative to the
 # flop-weighted mean (B200, benchmark system, class-major aux order; scripts/calibrate_lc_weights.py ->
 # profiles/r02_lc_weights.json).  Low Lc runs below the mean rate (fewer integrals per primitive-level recurrence).
-LC_TIME_WEIGHT = (1.397, 1.072, 0.968, 0.894, 0.914, 1.008)
+LC_TIME_WEIGHT = (1.313, 1.088, 0.978, 0.900, 0.918, 1.012)
 
 
 def aux_shell_costs(orb_shells, aux_shells, weights=LC_TIME_WEIGHT):
