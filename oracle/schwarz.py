@@ -9,9 +9,12 @@ Molecular Electronic-Structure Theory, sections 9.5 and 9.9):
 
     (ab|cd) = 2 pi^2.5 / (p q sqrt(p+q)) sum_{tuv} E^{ab}_{tuv} sum_{t'u'v'} (-1)^{t'+u'+v'} E^{cd}_{t'u'v'} R_{t+t',u+u',v+v'}(alpha, P-Q)
 
-It is checked (tests/test_schwarz.py) against the closed form for s functions, against numerical differentiation of
-lower angular momenta, against the PINNED 2c2e/3c2e oracles through the Cauchy-Schwarz inequality
-|(ab|P)|^2 <= (ab|ab)(P|P), and for positivity.  Only the diagonal (ab|ab) is exposed.
+``eri_block_os`` restates the reference's own transformations of that file literally (vrr0, vrr2, hrr1, hrr3 and the four
+C2S steps, int_4c2e.py:21-75) -- the algorithm the reference would run -- and agrees with the McMurchie-Davidson
+evaluation on every element of full four-index blocks to 1e-12 (tests/test_schwarz.py).  Further checks there: the
+closed form for s functions, numerical differentiation of lower angular momenta, the PINNED 2c2e/3c2e oracles through
+the Cauchy-Schwarz inequality |(ab|P)|^2 <= (ab|ab)(P|P), and positivity.  What stays impossible is a comparison with
+reference OUTPUT, hence "unpinned".
 """
 import numpy as np
 
@@ -116,6 +119,111 @@ def eri_block(Ls, bra, ket, sph=True, normalize="cgto", boys=None, diagonal=Fals
             else:
                 val = np.einsum("ijtuv,tuvxyz,klxyz->ijkl", EP, M, EQs) * pref
             out = val if out is None else out + val
+    return out
+
+
+def eri_block_os(Ls, bra, ket, sph=True, normalize="cgto", boys=None):
+    """(ab|cd) by a LITERAL restatement of the reference's transformations (sympleints/graphs/defs/int_4c2e.py):
+
+        base   2 pi^2.5 / (px qx sqrt(px+qx)) K_AB K_CD F_n(rho |PQ|^2)                                  (:21-23)
+        vrr0   [a+1_i 0|c 0]^n = PA_i [a|c]^n - qx/(px+qx) PQ_i [a|c]^{n+1}
+                                 + a_i/(2 px) ([a-1_i|c]^n - qx/(px+qx) [a-1_i|c]^{n+1})
+                                 + c_i/(2 (px+qx)) [a|c-1_i]^{n+1}                                      (:25-35)
+        vrr2   [a 0|c+1_i 0]^n = QC_i [a|c]^n + px/(px+qx) PQ_i [a|c]^{n+1}
+                                 + c_i/(2 qx) ([a|c-1_i]^n - px/(px+qx) [a|c-1_i]^{n+1})
+                                 + a_i/(2 (px+qx)) [a-1_i|c]^{n+1}                                      (:37-47)
+        hrr1   (a b+1_i|..) = (a+1_i b|..) + AB_i (a b|..)      hrr3   (..|c d+1_i) = (..|c+1_i d) + CD_i (..|c d)   (:49-68)
+        c2s on all four indices                                                                           (:55-74)
+
+    evaluated by memoised recursion per primitive quadruple (plain Python: small angular momenta only).  An algorithm
+    independent of the McMurchie-Davidson evaluation of eri_block; tests/test_schwarz.py checks that the two agree."""
+    import itertools
+    from functools import lru_cache
+
+    boys = boys or oboys.boys
+    if normalize not in ("cgto", "none"):
+        raise ValueError("eri_block_os: cgto / none only")
+    La, Lb, Lc, Ld = Ls
+    (ax, da, A, bx, db, B), (cx, dc, C, dx, dd, D) = bra, ket
+    ax, da, bx, db, cx, dc, dx, dd = (np.asarray(x, dtype=float).reshape(-1) for x in (ax, da, bx, db, cx, dc, dx, dd))
+    A, B, C, D = (np.asarray(x, dtype=float) for x in (A, B, C, D))
+    AB, CD = A - B, C - D
+    a_shells = [canonical_order(n) for n in range(La + Lb + 1)]
+    c_shells = [canonical_order(n) for n in range(Lc + Ld + 1)]
+    acc = {}
+    for (a, d1), (b, d2), (c, d3), (d, d4) in itertools.product(zip(ax, da), zip(bx, db), zip(cx, dc), zip(dx, dd)):
+        px, qx = a + b, c + d
+        P, Q = (a * A + b * B) / px, (c * C + d * D) / qx
+        PA, QC, PQ = P - A, Q - C, P - Q
+        KAB, KCD = np.exp(-a * b / px * AB @ AB), np.exp(-c * d / qx * CD @ CD)
+        rho = px * qx / (px + qx)
+        pre = 2 * np.pi**2.5 / (px * qx * np.sqrt(px + qx)) * KAB * KCD * d1 * d2 * d3 * d4
+        nmax = La + Lb + Lc + Ld
+        F = [pre * float(boys(n, rho * PQ @ PQ)) for n in range(nmax + 1)]
+
+        @lru_cache(maxsize=None)
+        def I(av, cv, n):
+            if min(av) < 0 or min(cv) < 0:
+                return 0.0
+            if sum(av) == 0 and sum(cv) == 0:
+                return F[n]
+            if sum(av) > 0:
+                i = next(k for k in range(3) if av[k] > 0)
+                am = tuple(av[k] - (k == i) for k in range(3))
+                amm = tuple(am[k] - (k == i) for k in range(3))
+                cm = tuple(cv[k] - (k == i) for k in range(3))
+                val = PA[i] * I(am, cv, n) - qx / (px + qx) * PQ[i] * I(am, cv, n + 1)
+                if am[i] > 0:
+                    val += am[i] / (2 * px) * (I(amm, cv, n) - qx / (px + qx) * I(amm, cv, n + 1))
+                if cv[i] > 0:
+                    val += cv[i] / (2 * (px + qx)) * I(am, cm, n + 1)
+                return val
+            i = next(k for k in range(3) if cv[k] > 0)
+            cm = tuple(cv[k] - (k == i) for k in range(3))
+            cmm = tuple(cm[k] - (k == i) for k in range(3))
+            val = QC[i] * I(av, cm, n) + px / (px + qx) * PQ[i] * I(av, cm, n + 1)
+            if cm[i] > 0:
+                val += cm[i] / (2 * qx) * (I(av, cmm, n) - px / (px + qx) * I(av, cmm, n + 1))
+            return val                      # (a == 0 here: the a_i / (2 (px+qx)) term vanishes)
+
+        for na in range(La, La + Lb + 1):
+            for av in a_shells[na]:
+                for nc in range(Lc, Lc + Ld + 1):
+                    for cv in c_shells[nc]:
+                        acc[(av, cv)] = acc.get((av, cv), 0.0) + I(av, cv, 0)
+
+    def hrr_b(av, bv, cv):              # (a b | c 0), contracted
+        if sum(bv) == 0:
+            return acc[(av, cv)]
+        i = next(k for k in range(3) if bv[k] > 0)
+        bm = tuple(bv[k] - (k == i) for k in range(3))
+        ap = tuple(av[k] + (k == i) for k in range(3))
+        return hrr_b(ap, bm, cv) + AB[i] * hrr_b(av, bm, cv)
+
+    ab_c = {}
+
+    def hrr_d(av, bv, cv, dv):
+        if sum(dv) == 0:
+            key = (av, bv, cv)
+            if key not in ab_c:
+                ab_c[key] = hrr_b(av, bv, cv)
+            return ab_c[key]
+        i = next(k for k in range(3) if dv[k] > 0)
+        dm = tuple(dv[k] - (k == i) for k in range(3))
+        cp = tuple(cv[k] + (k == i) for k in range(3))
+        return hrr_d(av, bv, cp, dm) + CD[i] * hrr_d(av, bv, cv, dm)
+
+    comps = [canonical_order(L) for L in Ls]
+    out = np.zeros(tuple(len(c) for c in comps))
+    for (i, av), (j, bv), (k, cv), (l, dv) in itertools.product(*(enumerate(c) for c in comps)):
+        out[i, j, k, l] = hrr_d(tuple(av), tuple(bv), tuple(cv), tuple(dv))
+    if normalize == "cgto":
+        for axis, L in enumerate(Ls):
+            shape = [1, 1, 1, 1]
+            shape[axis] = -1
+            out = out * np.asarray(lmn_factors(L)).reshape(shape)
+    if sph:
+        out = np.einsum("ia,jb,kc,ld,abcd->ijkl", cart2sph(La), cart2sph(Lb), cart2sph(Lc), cart2sph(Ld), out)
     return out
 
 

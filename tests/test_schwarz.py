@@ -1,8 +1,10 @@
 """Schwarz integrals (ab|ab) (sympleints/graphs/defs/int_4c2e.py, l_iters.py:23-28).
 
-The reference has this integral only on its Fortran graph path, so the oracle (oracle/schwarz.py) is UNPINNED;
-these CPU tests tie it to what can be checked: the closed form for s functions, numerical differentiation, and the
-Cauchy-Schwarz inequality against the pinned 2c2e / 3c2e oracle.  The GPU tests compare the CUDA kernel with it."""
+The reference has this integral only on its Fortran graph path, so the oracle (oracle/schwarz.py) is UNPINNED (no
+reference OUTPUT exists to compare with); these CPU tests tie it to what can be checked: a literal restatement of the
+reference's own transformations (vrr0, vrr2, hrr1, hrr3, c2s of int_4c2e.py) against the McMurchie-Davidson evaluation,
+the closed form for s functions, numerical differentiation, and the Cauchy-Schwarz inequality against the pinned
+2c2e / 3c2e oracle.  The GPU tests compare the CUDA kernel with it."""
 import numpy as np
 import pytest
 
@@ -50,6 +52,41 @@ def test_angular_momentum_by_numerical_differentiation():
     e = np.array([h, 0, 0])
     d2 = (ssss(A + e) - 2 * ssss(A) + ssss(A - e)) / h**2
     assert abs(dss[0, 0, 0, 0] - (d2 / (4 * a * a) + ssss(A) / (2 * a))) <= 1e-5 * abs(dss[0, 0, 0, 0])
+
+
+def _rshell(rng, L, K):
+    ex = 10 ** rng.uniform(-0.5, 0.8, K)
+    return ex, ints.norm_cgto_lmn(rng.uniform(0.3, 1, K), ex, L), rng.uniform(-1, 1, 3)
+
+
+@pytest.mark.parametrize("Ls", [(0, 0, 0, 0), (1, 0, 0, 0), (1, 1, 1, 0), (2, 1, 1, 1), (2, 0, 1, 2), (3, 1, 2, 0), (2, 2, 2, 2)])
+def test_reference_recurrences_against_mcmurchie_davidson_full_blocks(Ls):
+    """(ab|cd) for four different contracted shells: the reference's Obara-Saika / HRR transformations
+    (graphs/defs/int_4c2e.py:21-75, restated literally in eri_block_os) and the McMurchie-Davidson evaluation the
+    Schwarz oracle and the CUDA kernel use are two independent algorithms; every element of the block must agree."""
+    rng = np.random.default_rng(sum(10**k * l for k, l in enumerate(Ls)))
+    s = [_rshell(rng, L, 2) for L in Ls]
+    bra, ket = (*s[0], *s[1]), (*s[2], *s[3])
+    o = schwarz.eri_block_os(Ls, bra, ket)
+    m = schwarz.eri_block(Ls, bra, ket)
+    assert o.shape == tuple(2 * L + 1 for L in Ls)
+    assert np.abs(o - m).max() <= 1e-12 * np.abs(m).max()
+    # Cartesian, un-normalised variant (no C2S, no lmn factors)
+    oc = schwarz.eri_block_os(Ls, bra, ket, sph=False, normalize="none")
+    mc = schwarz.eri_block(Ls, bra, ket, sph=False, normalize="none")
+    assert np.abs(oc - mc).max() <= 1e-12 * np.abs(mc).max()
+
+
+@pytest.mark.parametrize("La,Lb,tol", [(3, 2, 1e-12), (3, 3, 1e-10), (4, 1, 1e-12), (4, 3, 1e-10)])
+def test_schwarz_diagonal_against_the_reference_recurrences(La, Lb, tol):
+    """The diagonal (ab|ab) the oracle exposes against the diagonal of the block built with the reference's recurrences
+    (the HRR loses digits for f and g kets, SURVEY 7.2, hence the looser bound there)."""
+    rng = np.random.default_rng(10 * La + Lb)
+    a, b = _rshell(rng, La, 1), _rshell(rng, Lb, 2 if La + Lb < 7 else 1)
+    sh = (*a, *b)
+    d = schwarz.schwarz_block(La, Lb, *sh)
+    o = np.einsum("ijij->ij", schwarz.eri_block_os((La, Lb, La, Lb), sh, sh))
+    assert (d > 0).all() and np.abs(o - d).max() <= tol * np.abs(d).max()
 
 
 @pytest.mark.parametrize("Ls", [(1, 0, 1), (2, 1, 2), (2, 2, 3), (3, 1, 0), (3, 3, 4)])
