@@ -133,6 +133,18 @@ def test_schwarz_kernel_against_the_oracle_and_the_inequality():
         g = D[off[i]:off[i + 1], off[j]:off[j + 1]]
         assert np.abs(g - o).max() <= 1e-14 + 1e-11 * np.abs(o).max(), (i, j, a.L, b.L)
         assert abs(Q[i, j] - np.sqrt(np.abs(o).max())) <= 1e-11 * Q[i, j]
+    # ... and directly against the literal restatement of the reference's recurrences (one pair per class up to f)
+    seen = set()
+    for (i, j) in pairs:
+        a, b = shells[i], shells[j]
+        if a.L > 3 or b.L > 3 or (a.L, b.L) in seen or len(a.exps) * len(b.exps) > 6:
+            continue
+        seen.add((a.L, b.L))
+        sh = (a.exps, a.coeffs, a.center, b.exps, b.coeffs, b.center)
+        o = np.einsum("ijij->ij", schwarz.eri_block_os((a.L, b.L, a.L, b.L), sh, sh, boys=bf))
+        g = D[off[i]:off[i + 1], off[j]:off[j + 1]]
+        assert np.abs(g - o).max() <= 1e-14 + 1e-10 * np.abs(o).max(), (i, j, a.L, b.L)
+    assert len(seen) >= 10
     T = eng.int3c2e(ob, ab, layout="full").cpu().numpy()
     M = eng.int2c2e(ab).cpu().numpy()
     bound = D[:, :, None] * np.diag(M)[None, None, :]
